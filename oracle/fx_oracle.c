@@ -1,0 +1,583 @@
+/*
+ * fx_oracle.c -- CPU restatement of frontx.solve (forward shooting solve).
+ *
+ * TEST INFRASTRUCTURE ONLY (see fx_oracle.h).  PARITY UNPINNED at 1e-6.
+ *
+ * Follows, in the reference tree /root/reference:
+ *   src/frontx/_forward.py:60-122   solve(): event, shoot(), Bisection call, status
+ *   src/frontx/_boltzmann.py:15-35  ode(): right-hand side
+ *   src/frontx/models.py:17-24,62-66,88-100,160-174,217-253,298-315  D(theta) families
+ * and restates the published algorithms of the un-vendored dependencies the
+ * reference delegates to (pyproject.toml:28-38):
+ *   diffrax >=0.7,<0.8   Kvaerno5 (7-stage ESDIRK 5(4), Kvaerno 2004), AbstractESDIRK stage
+ *                        loop with the chord ("VeryChord") root finder, PIDController
+ *                        (I-controller, Hairer initial step), boolean Event, cubic Hermite
+ *                        dense output;
+ *   optimistix >=0.0.10  Bisection(rtol=inf, atol=itol, expand_if_necessary=True);
+ *   lineax               LU with partial pivoting for the 2x2 chord system.
+ *
+ * Written as plain nested loops (bisection > steps > stages > chord), one
+ * problem at a time, libm pow/log for the model functions and Taylor jets for
+ * the derivatives the reference obtains by jax autodiff.  No attempt is made
+ * to be fast: this is the checker and the CPU timing baseline.
+ */
+#include "fx_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <stdatomic.h>
+#include <unistd.h>
+
+/* ------------------------------------------------------------------------- */
+/* Taylor jets (value, 1st, 2nd, 3rd derivative wrt theta): what jax.grad /  */
+/* jax.value_and_grad / jacfwd compute for the reference, done by hand.       */
+/* ------------------------------------------------------------------------- */
+typedef struct { double v, d1, d2, d3; } jet;
+
+static jet j_const(double c) { jet r = {c, 0.0, 0.0, 0.0}; return r; }
+static jet j_add(jet a, jet b) { jet r = {a.v + b.v, a.d1 + b.d1, a.d2 + b.d2, a.d3 + b.d3}; return r; }
+static jet j_sub(jet a, jet b) { jet r = {a.v - b.v, a.d1 - b.d1, a.d2 - b.d2, a.d3 - b.d3}; return r; }
+static jet j_neg(jet a) { jet r = {-a.v, -a.d1, -a.d2, -a.d3}; return r; }
+static jet j_scale(double c, jet a) { jet r = {c * a.v, c * a.d1, c * a.d2, c * a.d3}; return r; }
+static jet j_mul(jet a, jet b) {
+  jet r;
+  r.v = a.v * b.v;
+  r.d1 = a.d1 * b.v + a.v * b.d1;
+  r.d2 = a.d2 * b.v + 2.0 * a.d1 * b.d1 + a.v * b.d2;
+  r.d3 = a.d3 * b.v + 3.0 * a.d2 * b.d1 + 3.0 * a.d1 * b.d2 + a.v * b.d3;
+  return r;
+}
+/* composition phi(x) given phi', phi'', phi''' at x.v (Faa di Bruno to order 3) */
+static jet j_compose(jet x, double p0, double p1, double p2, double p3) {
+  jet r;
+  r.v = p0;
+  r.d1 = p1 * x.d1;
+  r.d2 = p2 * x.d1 * x.d1 + p1 * x.d2;
+  r.d3 = p3 * x.d1 * x.d1 * x.d1 + 3.0 * p2 * x.d1 * x.d2 + p1 * x.d3;
+  return r;
+}
+static jet j_recip(jet x) {
+  double r1 = 1.0 / x.v;
+  return j_compose(x, r1, -r1 * r1, 2.0 * r1 * r1 * r1, -6.0 * r1 * r1 * r1 * r1);
+}
+static jet j_div(jet a, jet b) { return j_mul(a, j_recip(b)); }
+/* x ** a with a a real constant: jax differentiates pow(x,a) as a*pow(x,a-1) */
+static jet j_powc(jet x, double a) {
+  return j_compose(x, pow(x.v, a), a * pow(x.v, a - 1.0), a * (a - 1.0) * pow(x.v, a - 2.0),
+                   a * (a - 1.0) * (a - 2.0) * pow(x.v, a - 3.0));
+}
+static jet j_log(jet x) {
+  double r1 = 1.0 / x.v;
+  return j_compose(x, log(x.v), r1, -r1 * r1, 2.0 * r1 * r1 * r1);
+}
+/* derivative jet: (f', f'', f''', unknown) */
+static jet j_deriv(jet a) { jet r = {a.d1, a.d2, a.d3, 0.0}; return r; }
+
+/* models.py:17-24  _Se */
+static jet Se_of(double theta, double theta_r, double theta_s) {
+  jet r = {(theta - theta_r) / (theta_s - theta_r), 1.0 / (theta_s - theta_r), 0.0, 0.0};
+  return r;
+}
+
+/* D(theta) as a jet, from the reference definitions */
+static jet D_jet(int model, const double *p, double theta) {
+  jet th = {theta, 1.0, 0.0, 0.0};
+  jet one = j_const(1.0);
+  switch (model) {
+    case FXO_CONSTANT:
+      return j_const(p[0]);
+    case FXO_POWER_LAW: /* fronts.D.power_law: a*theta**k + epsilon (no reference class) */
+      return j_add(j_scale(p[0], j_powc(th, p[1])), j_const(p[2]));
+    case FXO_LOG: /* tests/test_solve.py:40  D = (1 - log(theta))/2  ->  c0 + c1*log(theta) */
+      return j_add(j_const(p[0]), j_scale(p[1], j_log(th)));
+    case FXO_LETD: { /* models.py:62-66 */
+      double L = p[0], E = p[1], T = p[2], Dwt = p[3];
+      jet Se = Se_of(theta, p[4], p[5]);
+      jet A = j_powc(Se, L);
+      jet B = j_powc(j_sub(one, Se), T);
+      return j_div(j_scale(Dwt, A), j_add(A, j_scale(E, B)));
+    }
+    case FXO_BROOKS_COREY: { /* models.py:160-174, D = K/C, C = 1/(dh/dtheta)  :88-100 */
+      double n = p[0], l = p[1], Ks = p[2], alpha = p[3];
+      jet Se = Se_of(theta, p[4], p[5]);
+      jet h = j_neg(j_recip(j_scale(alpha, j_powc(Se, 1.0 / n))));
+      jet kr = j_powc(Se, 2.0 / n + l + 2.0);
+      jet C = j_recip(j_deriv(h));
+      return j_div(j_scale(Ks, kr), C);
+    }
+    case FXO_VAN_GENUCHTEN: { /* models.py:217-253 */
+      double n = p[0], m = p[1], l = p[2], Ks = p[3], alpha = p[4];
+      jet Se = Se_of(theta, p[5], p[6]);
+      jet u = j_powc(Se, 1.0 / m);
+      jet h = j_scale(-1.0 / alpha, j_powc(j_sub(j_recip(u), one), 1.0 / n));
+      jet w = j_sub(one, j_powc(j_sub(one, u), m));
+      jet kr = j_mul(j_powc(Se, l), j_mul(w, w));
+      jet C = j_recip(j_deriv(h));
+      return j_div(j_scale(Ks, kr), C);
+    }
+    case FXO_LETXS: { /* models.py:298-315 */
+      double Lw = p[0], Ew = p[1], Tw = p[2], Ls = p[3], Es = p[4], Ts = p[5], Ks = p[6], alpha = p[7];
+      jet Se = Se_of(theta, p[8], p[9]);
+      jet oms = j_sub(one, Se);
+      jet A = j_powc(Se, Lw);
+      jet kr = j_div(A, j_add(A, j_scale(Ew, j_powc(oms, Tw))));
+      jet P = j_powc(oms, Ls);
+      jet h = j_scale(-1.0 / alpha, j_div(P, j_add(P, j_scale(Es, j_powc(Se, Ts)))));
+      jet C = j_recip(j_deriv(h));
+      return j_div(j_scale(Ks, kr), C);
+    }
+    default:
+      return j_const(NAN);
+  }
+}
+
+void fxo_D(int model, const double *p, double theta, double *out) {
+  jet d = D_jet(model, p, theta);
+  out[0] = d.v;
+  out[1] = d.d1;
+  out[2] = d.d2;
+}
+
+/* ------------------------------------------------------------------------- */
+/* ODE right-hand side and its Jacobian                                      */
+/* ------------------------------------------------------------------------- */
+typedef struct {
+  int model;
+  const double *p;
+  int radial_k;
+  double rtol, atol;
+  int32_t n_rhs, n_jac;
+} ctx_t;
+
+/* _boltzmann.py:27-33: [p, -((o/2 + D' p)/D) p]; radial term k/o per fronts (Appendix E) */
+static void rhs(ctx_t *c, double o, const double *y, double *f) {
+  jet D = D_jet(c->model, c->p, y[0]);
+  double br = (o / 2.0 + D.d1 * y[1]) / D.v;
+  if (c->radial_k) br += (double)c->radial_k / o;
+  f[0] = y[1];
+  f[1] = -br * y[1];
+  c->n_rhs++;
+}
+void fxo_rhs(int model, const double *p, int radial_k, double o, const double *y, double *f) {
+  ctx_t c = {model, p, radial_k, 0, 0, 0, 0};
+  rhs(&c, o, y, f);
+}
+
+/* df/dy at (o,y): what lineax materialises from jacfwd of the stage relation */
+static void rhs_jac(ctx_t *c, double o, const double *y, double J[2][2]) {
+  jet D = D_jet(c->model, c->p, y[0]);
+  double th_p = y[1];
+  double num = o / 2.0 + D.d1 * th_p;
+  J[0][0] = 0.0;
+  J[0][1] = 1.0;
+  J[1][0] = -th_p * (D.d2 * th_p * D.v - num * D.d1) / (D.v * D.v);
+  J[1][1] = -(o / 2.0 + 2.0 * D.d1 * th_p) / D.v;
+  if (c->radial_k) J[1][1] -= (double)c->radial_k / o;
+  c->n_jac++;
+}
+
+/* ------------------------------------------------------------------------- */
+/* Kvaerno5 tableau (diffrax/_solver/kvaerno5.py; Kvaerno 2004)              */
+/* ------------------------------------------------------------------------- */
+#define GAMMA 0.26
+static const double A_LOW[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.26, 0, 0, 0, 0, 0},
+    {0.13, 0.84033320996790809, 0, 0, 0, 0},
+    {0.22371961478320505, 0.47675532319799699, -0.06470895363112615, 0, 0, 0},
+    {0.16648564323248321, 0.10450018841591720, 0.03631482272098715, -0.13090704451073998, 0, 0},
+    {0.13855640231268224, 0, -0.04245337201752043, 0.02446657898003141, 0.61943039072480676, 0},
+    {0.13659751177640291, 0, -0.05496908796538376, -0.04118626728321046, 0.62993304899016403,
+     0.06962479448202728}};
+static const double C_NODE[7] = {0.0, 0.52, 1.230333209967908, 0.8957659843500759,
+                                 0.43639360985864756, 1.0, 1.0};
+/* stage predictors (extrapolation of earlier stage derivatives) */
+static const double A_PRED[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0, 0, 0, 0, 0, 0},
+    {-1.366025403784441, 2.3660254037844357, 0, 0, 0, 0},
+    {-0.19650552613122207, 0.8113579546496623, 0.38514757148155954, 0, 0, 0},
+    {0.10375304369958693, 0.937994698066431, -0.04174774176601781, 0, 0, 0},
+    {-0.17281112873898072, 0.6235784481025847, 0.5492326806363959, 0, 0, 0},
+    {0.13855640231268224, 0, -0.04245337201752043, 0.02446657898003141, 0.61943039072480676,
+     GAMMA}};
+/* b_error = b_sol - b_embedded, b_sol = row 7 + gamma, b_embedded = row 6 + gamma */
+static const double B_ERR[7] = {0.13659751177640291 - 0.13855640231268224,
+                                0.0,
+                                -0.05496908796538376 - (-0.04245337201752043),
+                                -0.04118626728321046 - 0.02446657898003141,
+                                0.62993304899016403 - 0.61943039072480676,
+                                0.06962479448202728 - GAMMA,
+                                GAMMA};
+
+static double rms2(double a, double b) { return sqrt(a * a + b * b) / sqrt(2.0); }
+
+/* 2x2 LU with partial pivoting (lineax.LU -> jax lu_factor/lu_solve) */
+typedef struct { double l10, u00, u01, u11; int swap; } lu2;
+static void lu2_factor(double M[2][2], lu2 *f) {
+  f->swap = fabs(M[1][0]) > fabs(M[0][0]);
+  double a = M[0][0], b = M[0][1], c = M[1][0], d = M[1][1];
+  if (f->swap) { double t; t = a; a = c; c = t; t = b; b = d; d = t; }
+  f->u00 = a; f->u01 = b;
+  f->l10 = c / a;
+  f->u11 = d - f->l10 * b;
+}
+static void lu2_solve(const lu2 *f, const double *r, double *x) {
+  double r0 = r[0], r1 = r[1];
+  if (f->swap) { double t = r0; r0 = r1; r1 = t; }
+  double z1 = r1 - f->l10 * r0;
+  x[1] = z1 / f->u11;
+  x[0] = (r0 - f->u01 * x[1]) / f->u00;
+}
+
+/* Chord iteration for one implicit stage, unknown = stage derivative f:
+ *   r(f) = vf(ts, ypart + gamma*(dt*f)) - f = 0      (diffrax _implicit_relation_f)
+ * Termination (optimistix Chord/diffrax VeryChord): tested before every
+ * iteration once two have been taken; at most 10 iterations. 1 = success. */
+static int chord_solve(ctx_t *c, double ts, const double *ypart, double dt, const lu2 *J, double *f) {
+  const double kappa = 1e-2;
+  double diffsize = INFINITY, diffsize_prev = INFINITY;
+  for (int step = 0;; step++) {
+    if (step >= 2) {
+      double rate = diffsize / diffsize_prev;
+      double factor = diffsize * rate / (1.0 - rate);
+      int small = diffsize < 1e-13; /* 10**(2 - finfo(float64).precision) */
+      int diverged = !isfinite(rate) || rate > 2.0;
+      int converged = (factor > 0.0) && (factor < kappa);
+      if (small || diverged || converged) return (small || (converged && !diverged)) ? 1 : 0;
+    }
+    if (step >= 10) return 0; /* root_find_max_steps = 10 */
+    double ys[2] = {ypart[0] + GAMMA * (dt * f[0]), ypart[1] + GAMMA * (dt * f[1])};
+    double F[2], r[2], diff[2];
+    rhs(c, ts, ys, F);
+    r[0] = F[0] - f[0];
+    r[1] = F[1] - f[1];
+    lu2_solve(J, r, diff);
+    f[0] -= diff[0];
+    f[1] -= diff[1];
+    double s0 = c->atol + c->rtol * fabs(f[0]);
+    double s1 = c->atol + c->rtol * fabs(f[1]);
+    diffsize_prev = diffsize;
+    diffsize = rms2(diff[0] / s0, diff[1] / s1);
+  }
+}
+
+/* One Kvaerno5 step attempt from (t0,y0) with stage-1 derivative f0 (FSAL).
+ * Returns 1 when every stage solve succeeded.  y1 is the stiffly accurate
+ * stage-7 value, f7 its stage derivative (next step's f0), yerr the embedded
+ * error estimate. */
+static int kv5_attempt(ctx_t *c, double t0, double dt, const double *y0, const double *f0,
+                       double *y1, double *yerr, double *f7) {
+  double fs[7][2];
+  lu2 J;
+  double ypart[2];
+  fs[0][0] = f0[0];
+  fs[0][1] = f0[1];
+  for (int s = 1; s < 7; s++) {
+    double acc[2] = {0, 0}, fp[2] = {0, 0};
+    for (int j = 0; j < s; j++) {
+      acc[0] += A_LOW[s][j] * fs[j][0];
+      acc[1] += A_LOW[s][j] * fs[j][1];
+      fp[0] += A_PRED[s][j] * fs[j][0];
+      fp[1] += A_PRED[s][j] * fs[j][1];
+    }
+    ypart[0] = y0[0] + dt * acc[0];
+    ypart[1] = y0[1] + dt * acc[1];
+    double ts = t0 + C_NODE[s] * dt;
+    if (s == 1) { /* one Jacobian per attempt, at the first implicit stage's predicted point */
+      double ys[2] = {ypart[0] + GAMMA * (dt * fp[0]), ypart[1] + GAMMA * (dt * fp[1])};
+      double Jf[2][2], M[2][2];
+      rhs_jac(c, ts, ys, Jf);
+      M[0][0] = GAMMA * dt * Jf[0][0] - 1.0;
+      M[0][1] = GAMMA * dt * Jf[0][1];
+      M[1][0] = GAMMA * dt * Jf[1][0];
+      M[1][1] = GAMMA * dt * Jf[1][1] - 1.0;
+      lu2_factor(M, &J);
+    }
+    if (!chord_solve(c, ts, ypart, dt, &J, fp)) return 0;
+    fs[s][0] = fp[0];
+    fs[s][1] = fp[1];
+  }
+  y1[0] = ypart[0] + GAMMA * (dt * fs[6][0]);
+  y1[1] = ypart[1] + GAMMA * (dt * fs[6][1]);
+  double e[2] = {0, 0};
+  for (int j = 0; j < 7; j++) {
+    e[0] += B_ERR[j] * fs[j][0];
+    e[1] += B_ERR[j] * fs[j][1];
+  }
+  yerr[0] = dt * e[0];
+  yerr[1] = dt * e[1];
+  f7[0] = fs[6][0];
+  f7[1] = fs[6][1];
+  return 1;
+}
+
+/* diffrax _select_initial_step (Hairer-Norsett-Wanner II.4), error_order = 5 */
+static double initial_step(ctx_t *c, double t0, const double *y0, const double *f0) {
+  double sc0 = c->atol + fabs(y0[0]) * c->rtol, sc1 = c->atol + fabs(y0[1]) * c->rtol;
+  double d0 = rms2(y0[0] / sc0, y0[1] / sc1);
+  double d1 = rms2(f0[0] / sc0, f0[1] / sc1);
+  int cond = (d0 < 1e-5) || (d1 < 1e-5);
+  double h0 = cond ? 1e-6 : 0.01 * (d0 / d1);
+  double y1[2] = {y0[0] + h0 * f0[0], y0[1] + h0 * f0[1]}, f1[2];
+  rhs(c, t0 + h0, y1, f1);
+  double d2 = rms2((f1[0] - f0[0]) / sc0, (f1[1] - f0[1]) / sc1) / h0;
+  double max_d = fmax(d1, d2);
+  double h1 = (max_d <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / max_d, 1.0 / 5.0);
+  return fmin(100.0 * h0, h1);
+}
+
+void fxo_default_options(fxo_options *opt) {
+  opt->rtol = 1e-3;
+  opt->atol = 1e-6;
+  opt->max_ode_steps = 4096;
+  opt->max_expansions = 64;
+  opt->radial_k = 0;
+  opt->ob = 0.0;
+}
+
+/* shoot(): one diffeqsolve with the boolean event (_forward.py:76-102) */
+typedef struct { double residual, t_end, theta_end; } shot_t;
+static shot_t shoot(int model, const double *p, double b, double i, double itol, double d_dob,
+                    const fxo_options *opt, int k_max, double *knots, int *n_knots_out,
+                    int32_t *counters) {
+  ctx_t c = {model, p, opt->radial_k, opt->rtol, opt->atol, 0, 0};
+  double direction = (i > b) - (i < b); /* jnp.sign(i - b) */
+  double t0 = opt->ob, y0[2] = {b, d_dob}, f0[2];
+  int n_attempts = 0, n_rejected = 0, n_knots = 0, occurred = 0;
+
+  rhs(&c, t0, y0, f0); /* solver.init: f(t0,y0), also used by the step-size heuristic */
+  double dt = initial_step(&c, t0, y0, f0);
+  double t1 = t0 + dt;
+
+  if (knots && k_max > 0) {
+    double *k = knots;
+    k[0] = t0; k[1] = y0[0]; k[2] = y0[1]; k[3] = f0[0]; k[4] = f0[1];
+  }
+  n_knots = 1;
+
+  while (n_attempts < opt->max_ode_steps) {
+    double h = t1 - t0; /* terms.contr(t0,t1) */
+    double y1[2], yerr[2], f7[2] = {0.0, 0.0};
+    int ok = kv5_attempt(&c, t0, h, y0, f0, y1, yerr, f7);
+    n_attempts++;
+    /* failed implicit solve or NaN error  =>  err = inf  (reject, shrink) */
+    if (!ok) { yerr[0] = INFINITY; yerr[1] = INFINITY; y1[0] = y0[0]; y1[1] = y0[1]; }
+    if (isnan(yerr[0])) yerr[0] = INFINITY;
+    if (isnan(yerr[1])) yerr[1] = INFINITY;
+    /* PIDController (pcoeff=0, icoeff=1, dcoeff=0, safety 0.9, factormin 0.2, factormax 10) */
+    int nan1 = isnan(y1[0]) || isnan(y1[1]);
+    double a0 = nan1 ? y0[0] : y1[0], a1 = nan1 ? y0[1] : y1[1];
+    double sc0 = opt->atol + fmax(fabs(y0[0]), fabs(a0)) * opt->rtol;
+    double sc1 = opt->atol + fmax(fabs(y0[1]), fabs(a1)) * opt->rtol;
+    double err = rms2(yerr[0] / sc0, yerr[1] / sc1);
+    int keep = err < 1.0;
+    double inv = (err == 0.0) ? INFINITY : 1.0 / err;
+    double factor = 0.9 * pow(inv, 1.0 / 5.0);
+    double fmin_ = keep ? 1.0 : 0.2;
+    if (!(factor >= fmin_)) factor = fmin_; /* clip; NaN cannot occur (inv >= 0) */
+    if (factor > 10.0) factor = 10.0;
+    double dt_next = h * factor;
+    if (keep) {
+      t0 = t1;
+      y0[0] = y1[0]; y0[1] = y1[1];
+      f0[0] = f7[0]; f0[1] = f7[1];
+      if (knots && n_knots < k_max) {
+        double *k = knots + (size_t)FXO_KNOT * n_knots;
+        k[0] = t0; k[1] = y0[0]; k[2] = y0[1]; k[3] = f0[0]; k[4] = f0[1];
+      }
+      n_knots++;
+      /* event (_forward.py:76-78), evaluated on accepted states only */
+      if ((direction * y0[1] <= 0.0) || (direction * y0[0] > direction * (i - itol))) {
+        occurred = 1;
+        t1 = t0 + dt_next;
+        break;
+      }
+    } else {
+      n_rejected++;
+    }
+    t1 = t0 + dt_next;
+  }
+  if (n_knots_out) *n_knots_out = n_knots;
+  if (counters) {
+    counters[3] += n_attempts;
+    counters[4] += n_rejected;
+    counters[5] += c.n_rhs;
+    counters[6] += c.n_jac;
+    counters[7] = n_knots;
+  }
+  shot_t out;
+  out.residual = occurred ? (y0[0] - i) : direction * INFINITY; /* _forward.py:97-101 */
+  out.t_end = t0;
+  out.theta_end = y0[0];
+  return out;
+}
+
+double fxo_shoot(int model, const double *p, double b, double i, double itol, double d_dob,
+                 const fxo_options *opt_in, int k_max, double *knots, int *n_knots,
+                 int32_t *counters) {
+  fxo_options opt;
+  if (opt_in) opt = *opt_in; else fxo_default_options(&opt);
+  return shoot(model, p, b, i, itol, d_dob, &opt, k_max, knots, n_knots, counters).residual;
+}
+
+/* solve(): Bisection(rtol=inf, atol=itol, flip="detect", expand_if_necessary=True) on d_dob */
+int fxo_solve(int model, const double *p, double b, double i, double itol, int max_bisect,
+              const fxo_options *opt_in, double *summary, int32_t *counters, int k_max,
+              double *knots) {
+  fxo_options opt;
+  if (opt_in) opt = *opt_in; else fxo_default_options(&opt);
+  int32_t cnt[FXO_NCNT];
+  memset(cnt, 0, sizeof cnt);
+  double Db[3];
+  fxo_D(model, p, b, Db);
+  double lower = 0.0;
+  double upper = (i - b) / (2.0 * sqrt(Db[0])); /* _forward.py:110 */
+  int nk = 0;
+  shot_t last;
+  last = shoot(model, p, b, i, itol, lower, &opt, k_max, knots, &nk, cnt);
+  double r_lo = last.residual;
+  last = shoot(model, p, b, i, itol, upper, &opt, k_max, knots, &nk, cnt);
+  double r_hi = last.residual;
+  cnt[1] = 2;
+  int lo_neg = r_lo < 0.0, hi_neg = r_hi < 0.0;
+  int result = 0;
+  while (lo_neg == hi_neg) { /* expand_if_necessary (U6) */
+    if (cnt[2] >= opt.max_expansions) { result = 2; break; }
+    double w = upper - lower;
+    lower -= w;
+    upper += w;
+    last = shoot(model, p, b, i, itol, lower, &opt, k_max, knots, &nk, cnt);
+    r_lo = last.residual;
+    last = shoot(model, p, b, i, itol, upper, &opt, k_max, knots, &nk, cnt);
+    r_hi = last.residual;
+    cnt[1] += 2;
+    cnt[2]++;
+    lo_neg = r_lo < 0.0;
+    hi_neg = r_hi < 0.0;
+  }
+  double mid = upper, res = r_hi;
+  if (result == 0) {
+    result = 1; /* max_steps_reached unless the loop terminates */
+    for (int k = 0; k < max_bisect; k++) {
+      mid = lower + 0.5 * (upper - lower);
+      last = shoot(model, p, b, i, itol, mid, &opt, k_max, knots, &nk, cnt);
+      res = last.residual;
+      cnt[1]++;
+      if ((res < 0.0) == lo_neg) lower = mid; else upper = mid;
+      /* terminate: |upper-lower| < atol + rtol*|mid| (rtol = inf) AND |res| < atol */
+      double scale = itol + INFINITY * fabs(mid);
+      if ((fabs(upper - lower) < scale) && (fabs(res) < itol)) { result = 0; break; }
+    }
+  }
+  cnt[0] = result;
+  cnt[7] = nk;
+  if (summary) {
+    summary[0] = mid;
+    summary[1] = last.t_end;
+    summary[2] = last.theta_end;
+    summary[3] = -2.0 * Db[0] * mid;
+    summary[4] = Db[0];
+    summary[5] = res;
+    summary[6] = lower;
+    summary[7] = upper;
+  }
+  if (counters) memcpy(counters, cnt, sizeof cnt);
+  return result;
+}
+
+int fxo_num_threads(void) {
+  long n = sysconf(_SC_NPROCESSORS_ONLN);
+  return n > 0 ? (int)n : 1;
+}
+
+/* batch driver: plain pthreads pulling problems off a shared counter */
+typedef struct {
+  int64_t n;
+  const int32_t *model;
+  const double *params, *b, *i;
+  double itol;
+  int max_bisect;
+  const fxo_options *opt;
+  double *summary;
+  int32_t *counters;
+  int k_max;
+  double *knots;
+  atomic_llong next;
+  atomic_int bad;
+} batch_t;
+
+static void *batch_worker(void *arg) {
+  batch_t *B = (batch_t *)arg;
+  for (;;) {
+    int64_t j0 = atomic_fetch_add(&B->next, 4);
+    if (j0 >= B->n) break;
+    int64_t j1 = j0 + 4 < B->n ? j0 + 4 : B->n;
+    for (int64_t j = j0; j < j1; j++) {
+      int r = fxo_solve(B->model[j], B->params + (size_t)FXO_NPARAM * j, B->b[j], B->i[j], B->itol,
+                        B->max_bisect, B->opt,
+                        B->summary ? B->summary + (size_t)FXO_NSUM * j : NULL,
+                        B->counters ? B->counters + (size_t)FXO_NCNT * j : NULL, B->k_max,
+                        B->knots ? B->knots + (size_t)FXO_KNOT * B->k_max * j : NULL);
+      if (r != 0) atomic_fetch_add(&B->bad, 1);
+    }
+  }
+  return NULL;
+}
+
+int fxo_solve_batch(int64_t n, const int32_t *model, const double *params, const double *b,
+                    const double *i, double itol, int max_bisect, const fxo_options *opt,
+                    double *summary, int32_t *counters, int k_max, double *knots, int nthreads) {
+  if (nthreads <= 0) nthreads = fxo_num_threads();
+  if (nthreads > 256) nthreads = 256;
+  batch_t B = {n, model, params, b, i, itol, max_bisect, opt, summary, counters, k_max, knots, 0, 0};
+  pthread_t th[256];
+  int started = 0;
+  for (int t = 1; t < nthreads; t++) {
+    if (pthread_create(&th[started], NULL, batch_worker, &B) == 0) started++;
+  }
+  batch_worker(&B);
+  for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+  return atomic_load(&B.bad);
+}
+
+/* Solution.__call__ / d_do (_forward.py:25-37): clip to [0, oi], searchsorted(left),
+ * cubic Hermite of diffrax's ThirdOrderHermitePolynomialInterpolation.from_k */
+void fxo_eval(int n_knots, const double *knots, int64_t q, const double *o, double *theta,
+              double *dtheta_do) {
+  const double *K = knots;
+  double o_first = K[0], o_last = K[(size_t)FXO_KNOT * (n_knots - 1)];
+  for (int64_t j = 0; j < q; j++) {
+    double t = o[j];
+    if (t < o_first) t = o_first; /* jnp.clip(o, 0, oi); ts[0] = 0 for the reference */
+    if (t > o_last) t = o_last;
+    if (n_knots < 2) {
+      if (theta) theta[j] = K[1];
+      if (dtheta_do) dtheta_do[j] = K[2];
+      continue;
+    }
+    /* index = clip(searchsorted(ts, t, side="left") - 1, 0, len-2) */
+    int lo = 0, hi = n_knots;
+    while (lo < hi) {
+      int mid = (lo + hi) / 2;
+      if (K[(size_t)FXO_KNOT * mid] < t) lo = mid + 1; else hi = mid;
+    }
+    int idx = lo - 1;
+    if (idx < 0) idx = 0;
+    if (idx > n_knots - 2) idx = n_knots - 2;
+    const double *k0 = K + (size_t)FXO_KNOT * idx, *k1 = k0 + FXO_KNOT;
+    double dt = k1[0] - k0[0];
+    double s = (t - k0[0]) / ((dt == 0.0) ? 1.0 : dt);
+    for (int cpt = 0; cpt < 2; cpt++) {
+      double y0 = k0[1 + cpt], y1 = k1[1 + cpt];
+      double K0 = dt * k0[3 + cpt], K1 = dt * k1[3 + cpt];
+      double a = K0 + K1 + 2.0 * y0 - 2.0 * y1;
+      double bb = -2.0 * K0 - K1 - 3.0 * y0 + 3.0 * y1;
+      double v = ((a * s + bb) * s + K0) * s + y0;
+      if (cpt == 0) { if (theta) theta[j] = v; }
+      else { if (dtheta_do) dtheta_do[j] = v; }
+    }
+  }
+}

@@ -1,0 +1,172 @@
+"""ctypes binding of the CPU oracle (oracle/libfx_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / ``--impl reference`` legs of bench.py.  Nothing under
+``frontx_b200/`` may import this module.  PARITY UNPINNED at 1e-6 (see
+oracle/fx_oracle.h).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "libfx_oracle.so"
+
+NPARAM, NSUM, NCNT, KNOT = 12, 8, 8, 5
+
+CONSTANT, POWER_LAW, BROOKS_COREY, VAN_GENUCHTEN, LETXS, LETD, LOG = range(7)
+
+
+class Options(C.Structure):
+    _fields_ = [
+        ("rtol", C.c_double),
+        ("atol", C.c_double),
+        ("max_ode_steps", C.c_int),
+        ("max_expansions", C.c_int),
+        ("radial_k", C.c_int),
+        ("ob", C.c_double),
+    ]
+
+
+def build(force: bool = False) -> Path:
+    srcs = [HERE / "fx_oracle.c", HERE / "fx_oracle_inverse.c", HERE / "fx_oracle.h"]
+    stale = (not LIB.exists()) or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs)
+    if force or stale:
+        env = dict(os.environ)
+        env.pop("CC", None)
+        subprocess.run(["make", "-C", str(HERE), "-B"], check=True, env=env, capture_output=True)
+    return LIB
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB))
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int32)
+        L.fxo_default_options.argtypes = [C.POINTER(Options)]
+        L.fxo_D.argtypes = [C.c_int, dp, C.c_double, dp]
+        L.fxo_rhs.argtypes = [C.c_int, dp, C.c_int, C.c_double, dp, dp]
+        L.fxo_shoot.argtypes = [C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                C.POINTER(Options), C.c_int, dp, C.POINTER(C.c_int), ip]
+        L.fxo_shoot.restype = C.c_double
+        L.fxo_solve.argtypes = [C.c_int, dp, C.c_double, C.c_double, C.c_double, C.c_int,
+                                C.POINTER(Options), dp, ip, C.c_int, dp]
+        L.fxo_solve.restype = C.c_int
+        L.fxo_solve_batch.argtypes = [C.c_int64, ip, dp, dp, dp, C.c_double, C.c_int,
+                                      C.POINTER(Options), dp, ip, C.c_int, dp, C.c_int]
+        L.fxo_solve_batch.restype = C.c_int
+        L.fxo_eval.argtypes = [C.c_int, dp, C.c_int64, dp, dp, dp]
+        L.fxo_inverse.argtypes = [C.c_int64, dp, dp, dp, dp, dp]
+        L.fxo_inverse.restype = C.c_int
+        L.fxo_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def default_options(**kw) -> Options:
+    o = Options()
+    lib().fxo_default_options(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def pad_params(p) -> np.ndarray:
+    out = np.zeros(NPARAM, dtype=np.float64)
+    p = np.asarray(p, dtype=np.float64)
+    out[: p.size] = p
+    return out
+
+
+def D(model: int, params, theta) -> np.ndarray:
+    """(D, D', D'') at each theta; shape [..., 3]."""
+    p = pad_params(params)
+    th = np.atleast_1d(np.asarray(theta, dtype=np.float64))
+    out = np.empty((th.size, 3))
+    tmp = np.empty(3)
+    for k, t in enumerate(th.ravel()):
+        lib().fxo_D(model, _dp(p), float(t), _dp(tmp))
+        out[k] = tmp
+    return out.reshape(th.shape + (3,))
+
+
+def rhs(model: int, params, o: float, y, radial_k: int = 0) -> np.ndarray:
+    p = pad_params(params)
+    yy = np.asarray(y, dtype=np.float64).copy()
+    f = np.empty(2)
+    lib().fxo_rhs(model, _dp(p), radial_k, float(o), _dp(yy), _dp(f))
+    return f
+
+
+def solve(model: int, params, b: float, i: float, itol: float = 1e-3, max_steps: int = 100,
+          k_max: int = 512, options: Options | None = None):
+    """One problem. Returns dict(summary, counters, knots[n_knots,5])."""
+    p = pad_params(params)
+    summary = np.empty(NSUM)
+    counters = np.zeros(NCNT, dtype=np.int32)
+    knots = np.zeros((k_max, KNOT))
+    opt = options if options is not None else default_options()
+    lib().fxo_solve(model, _dp(p), float(b), float(i), float(itol), int(max_steps),
+                    C.byref(opt), _dp(summary), _ip(counters), k_max, _dp(knots))
+    nk = min(int(counters[7]), k_max)
+    return {"summary": summary, "counters": counters, "knots": knots[:nk].copy()}
+
+
+def solve_batch(model, params, b, i, itol: float = 1e-3, max_steps: int = 100, k_max: int = 0,
+                options: Options | None = None, nthreads: int = 0):
+    model = np.ascontiguousarray(model, dtype=np.int32)
+    n = model.size
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(n, NPARAM)
+    b = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float64), (n,)))
+    i = np.ascontiguousarray(np.broadcast_to(np.asarray(i, dtype=np.float64), (n,)))
+    summary = np.empty((n, NSUM))
+    counters = np.zeros((n, NCNT), dtype=np.int32)
+    knots = np.zeros((n, k_max, KNOT)) if k_max > 0 else None
+    opt = options if options is not None else default_options()
+    lib().fxo_solve_batch(n, _ip(model), _dp(params), _dp(b), _dp(i), float(itol), int(max_steps),
+                          C.byref(opt), _dp(summary), _ip(counters), k_max,
+                          _dp(knots) if knots is not None else None, int(nthreads))
+    return {"summary": summary, "counters": counters, "knots": knots}
+
+
+def evaluate(knots: np.ndarray, o) -> tuple[np.ndarray, np.ndarray]:
+    """theta(o), dtheta/do(o) from a [n_knots,5] table (Solution.__call__/d_do)."""
+    k = np.ascontiguousarray(knots, dtype=np.float64)
+    oo = np.ascontiguousarray(np.atleast_1d(o), dtype=np.float64)
+    th = np.empty(oo.size)
+    dth = np.empty(oo.size)
+    lib().fxo_eval(k.shape[0], _dp(k), oo.size, _dp(oo.ravel()), _dp(th), _dp(dth))
+    return th.reshape(oo.shape), dth.reshape(oo.shape)
+
+
+def inverse(o, theta):
+    oo = np.ascontiguousarray(o, dtype=np.float64)
+    th = np.ascontiguousarray(theta, dtype=np.float64)
+    Dk = np.empty(oo.size)
+    s1 = C.c_double()
+    s2 = C.c_double()
+    rc = lib().fxo_inverse(oo.size, _dp(oo), _dp(th), _dp(Dk), C.byref(s1), C.byref(s2))
+    return rc, Dk, s1.value, s2.value
+
+
+def num_threads() -> int:
+    return int(lib().fxo_num_threads())
