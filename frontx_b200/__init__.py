@@ -1,0 +1,34 @@
+"""frontx_b200 -- B200-native batched Boltzmann-transformed shooting solve.
+
+Drop-in for the hot path of gerlero/frontx: ``solve`` / ``Solution`` (plus the
+batched ``solve_batch``), the tagged diffusivity models, and the profile -> D
+inverse (``InterpolatedSolution``, ``sorptivity``, batched ``inverse``).  All
+compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/frontx_b200.h``; there is no CPU fallback.
+"""
+
+from . import D, models
+from ._forward import RESULTS, BatchSolution, Solution, SolveError, solve, solve_batch, solve_batch_host
+from ._inverse import BatchInverse, InterpolatedSolution, inverse, sorptivity
+from ._lib import FrontxB200Error
+from .models import ModelBatch
+
+__version__ = "0.1.0"
+
+__all__ = [
+    "RESULTS",
+    "BatchInverse",
+    "BatchSolution",
+    "D",
+    "FrontxB200Error",
+    "InterpolatedSolution",
+    "ModelBatch",
+    "Solution",
+    "SolveError",
+    "inverse",
+    "models",
+    "solve",
+    "solve_batch",
+    "solve_batch_host",
+    "sorptivity",
+]

@@ -1,0 +1,570 @@
+// fx_api.cu -- the C ABI of libfrontx_b200.so (include/frontx_b200.h) and the
+// host-side launch logic: device-side bucketing of a mixed batch by model, one
+// persistent launch per model on forked streams, the dense-output evaluation
+// and diffusivity kernels, and a DFMA micro-benchmark for the FP64 roofline.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/frontx_b200.h"
+#include "fx_inverse.cuh"
+#include "fx_solve.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_err, sizeof g_err, fmt, detail);
+  return code;
+}
+
+#define FX_CUDA(call)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return fail(FX_ERR_CUDA, #call ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DeviceInfo {
+  int sms = 0;
+  bool ok = false;
+};
+
+int device_info(DeviceInfo* out) {
+  int dev = 0;
+  FX_CUDA(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev < 0 || dev >= 64) return fail(FX_ERR_CUDA, "device index out of range%s");
+  if (!cache[dev].ok) {
+    FX_CUDA(cudaDeviceGetAttribute(&cache[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+    cache[dev].ok = true;
+  }
+  *out = cache[dev];
+  return FX_OK;
+}
+
+// ---- bucketing of a mixed batch by model -----------------------------------
+// scratch layout (unsigned long long): counts[8] | cursors[8] | queues[8]
+constexpr int SCR_COUNTS = 0, SCR_CURSORS = 8, SCR_QUEUES = 16, SCR_WORDS = 24;
+
+__global__ void count_models_kernel(long long n, const int* __restrict__ model_id,
+                                    unsigned long long* scratch) {
+  __shared__ unsigned int local[8];
+  if (threadIdx.x < 8) local[threadIdx.x] = 0;
+  __syncthreads();
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    int m = model_id[j];
+    if (m < 0 || m >= FX_NUM_MODELS) m = 7;  // invalid ids are parked in slot 7 and flagged
+    atomicAdd(&local[m], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 8 && local[threadIdx.x])
+    atomicAdd(&scratch[SCR_COUNTS + threadIdx.x], (unsigned long long)local[threadIdx.x]);
+}
+
+__global__ void scatter_models_kernel(long long n, const int* __restrict__ model_id,
+                                      unsigned long long* scratch, int* __restrict__ perm,
+                                      int* __restrict__ counters) {
+  // bucket-major placement; order inside a bucket is by warp-aggregated cursor
+  long long base[8];
+  long long acc = 0;
+  for (int k = 0; k < 8; k++) {
+    base[k] = acc;
+    acc += (long long)scratch[SCR_COUNTS + k];
+  }
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    int m = model_id[j];
+    if (m < 0 || m >= FX_NUM_MODELS) {
+      m = 7;
+      counters[j * FX_NCNT + 0] = -1;  // invalid model id: never solved
+    }
+    unsigned long long pos = atomicAdd(&scratch[SCR_CURSORS + m], 1ull);
+    perm[base[m] + (long long)pos] = (int)j;
+  }
+}
+
+template <int MODEL>
+int launch_model(const fx::SolveArgs& a, bool radial, int grid, cudaStream_t s) {
+  if (radial)
+    fx::shoot_bisect_kernel<MODEL, true><<<grid, fx::SOLVE_BLOCK, 0, s>>>(a);
+  else
+    fx::shoot_bisect_kernel<MODEL, false><<<grid, fx::SOLVE_BLOCK, 0, s>>>(a);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+template <int MODEL>
+int occupancy_of(bool radial, int* blocks) {
+  if (radial)
+    FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        blocks, fx::shoot_bisect_kernel<MODEL, true>, fx::SOLVE_BLOCK, 0));
+  else
+    FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        blocks, fx::shoot_bisect_kernel<MODEL, false>, fx::SOLVE_BLOCK, 0));
+  return FX_OK;
+}
+
+int launch_by_id(int model, const fx::SolveArgs& a, bool radial, long long n_upper, int sms,
+                 cudaStream_t s) {
+  int bps = 1, rc = FX_OK;
+  switch (model) {
+    case FX_CONSTANT: rc = occupancy_of<FX_CONSTANT>(radial, &bps); break;
+    case FX_POWER_LAW: rc = occupancy_of<FX_POWER_LAW>(radial, &bps); break;
+    case FX_BROOKS_COREY: rc = occupancy_of<FX_BROOKS_COREY>(radial, &bps); break;
+    case FX_VAN_GENUCHTEN: rc = occupancy_of<FX_VAN_GENUCHTEN>(radial, &bps); break;
+    case FX_LETXS: rc = occupancy_of<FX_LETXS>(radial, &bps); break;
+    case FX_LETD: rc = occupancy_of<FX_LETD>(radial, &bps); break;
+    case FX_LOG: rc = occupancy_of<FX_LOG>(radial, &bps); break;
+    default: return fail(FX_ERR_MODEL, "unknown model id%s");
+  }
+  if (rc) return rc;
+  if (bps < 1) bps = 1;
+  long long want = (n_upper + fx::SOLVE_BLOCK - 1) / fx::SOLVE_BLOCK;
+  long long cap = (long long)sms * bps;  // persistent grid: every CTA resident
+  int grid = (int)(want < cap ? want : cap);
+  if (grid < 1) grid = 1;
+  switch (model) {
+    case FX_CONSTANT: return launch_model<FX_CONSTANT>(a, radial, grid, s);
+    case FX_POWER_LAW: return launch_model<FX_POWER_LAW>(a, radial, grid, s);
+    case FX_BROOKS_COREY: return launch_model<FX_BROOKS_COREY>(a, radial, grid, s);
+    case FX_VAN_GENUCHTEN: return launch_model<FX_VAN_GENUCHTEN>(a, radial, grid, s);
+    case FX_LETXS: return launch_model<FX_LETXS>(a, radial, grid, s);
+    case FX_LETD: return launch_model<FX_LETD>(a, radial, grid, s);
+    default: return launch_model<FX_LOG>(a, radial, grid, s);
+  }
+}
+
+// per-device helper streams/events used to run the per-model launches side by side
+struct Fork {
+  cudaStream_t streams[FX_NUM_MODELS] = {};
+  cudaEvent_t begin = nullptr, done[FX_NUM_MODELS] = {};
+  cudaEvent_t k0[FX_NUM_MODELS] = {}, k1[FX_NUM_MODELS] = {};  // kernel timing (fx_set_kernel_timing)
+  bool timed[FX_NUM_MODELS] = {};
+  bool ok = false;
+};
+
+std::atomic<int> g_kernel_timing{0};
+
+int get_fork(Fork** out) {
+  int dev = 0;
+  FX_CUDA(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static Fork forks[64];
+  std::lock_guard<std::mutex> lk(mu);
+  Fork& f = forks[dev];
+  if (!f.ok) {
+    for (int m = 0; m < FX_NUM_MODELS; m++) {
+      FX_CUDA(cudaStreamCreateWithFlags(&f.streams[m], cudaStreamNonBlocking));
+      FX_CUDA(cudaEventCreateWithFlags(&f.done[m], cudaEventDisableTiming));
+      FX_CUDA(cudaEventCreate(&f.k0[m]));
+      FX_CUDA(cudaEventCreate(&f.k1[m]));
+    }
+    FX_CUDA(cudaEventCreateWithFlags(&f.begin, cudaEventDisableTiming));
+    f.ok = true;
+  }
+  *out = &f;
+  return FX_OK;
+}
+
+int check_options(const fx_solve_options* in, fx_solve_options* o) {
+  if (in) *o = *in; else fx_default_solve_options(o);
+  if (!(o->itol > 0.0) || o->max_bisect < 1 || o->max_ode_steps < 1 || !(o->rtol > 0.0) ||
+      !(o->atol >= 0.0) || o->max_expansions < 0)
+    return fail(FX_ERR_ARG, "invalid solve options%s");
+  if (o->radial_k < 0 || o->radial_k > 2) return fail(FX_ERR_ARG, "radial_k must be 0, 1 or 2%s");
+  if (o->radial_k > 0 && !(o->ob > 0.0)) return fail(FX_ERR_ARG, "radial problems need ob > 0%s");
+  return FX_OK;
+}
+
+// ---- dense output evaluation (Solution.__call__/d_do, _forward.py:25-37) -----
+__global__ void eval_kernel(long long n, const int* __restrict__ counters,
+                            const double* __restrict__ knots, int k_max, long long q,
+                            const double* __restrict__ o_query, int per_problem,
+                            double* __restrict__ theta, double* __restrict__ dtheta) {
+  long long total = n * q;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    long long j = g / q, c = g - j * q;
+    int nk = counters[j * FX_NCNT + 7];
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    double th = nan, dth = nan;
+    if (nk >= 1 && nk <= k_max) {
+      const double4* K = reinterpret_cast<const double4*>(knots + (size_t)j * k_max * FX_KNOT);
+      double t = o_query[per_problem ? g : c];
+      double4 first = K[0], last = K[nk - 1];
+      t = fmin(fmax(t, first.x), last.x);  // jnp.clip(o, 0, oi); NaN query stays NaN below
+      if (o_query[per_problem ? g : c] != o_query[per_problem ? g : c]) t = nan;
+      if (nk == 1) {
+        th = first.y;
+        dth = first.z;
+      } else {
+        // index = clip(searchsorted(ts, t, side="left") - 1, 0, nk-2)
+        int lo = 0, hi = nk;
+        while (lo < hi) {
+          int mid = (lo + hi) >> 1;
+          if (K[mid].x < t) lo = mid + 1; else hi = mid;
+        }
+        int idx = min(max(lo - 1, 0), nk - 2);
+        double4 a = K[idx], bb = K[idx + 1];
+        double dt = bb.x - a.x;
+        double s = (t - a.x) / ((dt == 0.0) ? 1.0 : dt);
+        {  // theta: k = dt * theta'
+          double k0 = dt * a.z, k1 = dt * bb.z;
+          double ca = k0 + k1 + 2.0 * a.y - 2.0 * bb.y;
+          double cb = -2.0 * k0 - k1 - 3.0 * a.y + 3.0 * bb.y;
+          th = fma(fma(fma(ca, s, cb), s, k0), s, a.y);
+        }
+        {  // dtheta/do is the SECOND STATE COMPONENT's interpolant: k = dt * theta''
+          double k0 = dt * a.w, k1 = dt * bb.w;
+          double ca = k0 + k1 + 2.0 * a.z - 2.0 * bb.z;
+          double cb = -2.0 * k0 - k1 - 3.0 * a.z + 3.0 * bb.z;
+          dth = fma(fma(fma(ca, s, cb), s, k0), s, a.z);
+        }
+      }
+    }
+    if (theta) theta[g] = th;
+    if (dtheta) dtheta[g] = dth;
+  }
+}
+
+// ---- D, D', D'' at arbitrary theta (Solution.D for flux/sorptivity) ----------
+template <int MODEL>
+__device__ void diffusivity_one(const double* p, double th, double* out) {
+  double d[fx::NDERIVED];
+  fx::derive_params<MODEL>(p, d);
+  double D, D1, D2;
+  fx::eval_D<MODEL>(d, th, true, D, D1, D2);
+  out[0] = D;
+  out[1] = D1;
+  out[2] = D2;
+}
+
+__global__ void diffusivity_kernel(long long n, const int* __restrict__ model_id,
+                                   const double* __restrict__ params, long long q,
+                                   const double* __restrict__ theta, double* __restrict__ out) {
+  long long total = n * q;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    long long j = g / q;
+    const double* p = params + j * FX_NPARAM;
+    double th = theta[g];
+    double* o = out + g * 3;
+    switch (model_id[j]) {
+      case FX_CONSTANT: diffusivity_one<FX_CONSTANT>(p, th, o); break;
+      case FX_POWER_LAW: diffusivity_one<FX_POWER_LAW>(p, th, o); break;
+      case FX_BROOKS_COREY: diffusivity_one<FX_BROOKS_COREY>(p, th, o); break;
+      case FX_VAN_GENUCHTEN: diffusivity_one<FX_VAN_GENUCHTEN>(p, th, o); break;
+      case FX_LETXS: diffusivity_one<FX_LETXS>(p, th, o); break;
+      case FX_LETD: diffusivity_one<FX_LETD>(p, th, o); break;
+      case FX_LOG: diffusivity_one<FX_LOG>(p, th, o); break;
+      default: o[0] = o[1] = o[2] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+  }
+}
+
+// ---- FP64 FMA throughput (roofline denominator) ------------------------------
+__global__ void dfma_peak_kernel(double* sink, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+  double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+#pragma unroll 1
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) sink[0] = s;
+}
+
+int grid_for(long long total, int block, int sms) {
+  long long want = (total + block - 1) / block;
+  long long cap = (long long)sms * 16;
+  long long g = want < cap ? want : cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" {
+
+void fx_default_solve_options(fx_solve_options* o) {
+  o->itol = 1e-3;
+  o->max_bisect = 100;
+  o->max_ode_steps = 4096;
+  o->rtol = 1e-3;
+  o->atol = 1e-6;
+  o->max_expansions = 64;
+  o->radial_k = 0;
+  o->ob = 0.0;
+}
+
+const char* fx_last_error(void) { return g_err; }
+int fx_version(void) { return FX_VERSION; }
+long long fx_launch_count_ll(void) { return g_launches.load(); }
+int64_t fx_launch_count(void) { return (int64_t)g_launches.load(); }
+
+void fx_set_kernel_timing(int on) { g_kernel_timing.store(on ? 1 : 0); }
+
+int fx_last_solve_kernel_ms(int model, float* ms) {
+  if (model < 0 || model >= FX_NUM_MODELS || !ms) return fail(FX_ERR_ARG, "bad model id or null pointer%s");
+  Fork* fk = nullptr;
+  int rc = get_fork(&fk);
+  if (rc) return rc;
+  if (!fk->timed[model]) return fail(FX_ERR_ARG, "no timed launch recorded: call fx_set_kernel_timing(1) first%s");
+  FX_CUDA(cudaEventSynchronize(fk->k1[model]));
+  FX_CUDA(cudaEventElapsedTime(ms, fk->k0[model], fk->k1[model]));
+  return FX_OK;
+}
+
+int fx_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, const double* b,
+                   const double* i, const fx_solve_options* opt_in, double* summary,
+                   int32_t* counters, int32_t k_max, double* knots, void* stream) {
+  if (n < 0 || k_max < 0) return fail(FX_ERR_ARG, "negative size%s");
+  if (n == 0) return FX_OK;
+  if (!model_id || !params || !b || !i || !summary || !counters)
+    return fail(FX_ERR_ARG, "null pointer argument%s");
+  if (k_max > 0 && !knots) return fail(FX_ERR_ARG, "k_max > 0 needs a knots buffer%s");
+  if (n > 2147483647LL) return fail(FX_ERR_ARG, "n exceeds 2^31-1 problems per call%s");
+  fx_solve_options o;
+  int rc = check_options(opt_in, &o);
+  if (rc) return rc;
+  DeviceInfo di;
+  if ((rc = device_info(&di))) return rc;
+  Fork* fk = nullptr;
+  if ((rc = get_fork(&fk))) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+
+  // scratch: bucket counters + permutation, stream-ordered
+  unsigned long long* scratch = nullptr;
+  int* perm = nullptr;
+  FX_CUDA(cudaMallocAsync((void**)&scratch, SCR_WORDS * sizeof(unsigned long long), s));
+  FX_CUDA(cudaMallocAsync((void**)&perm, (size_t)n * sizeof(int), s));
+  FX_CUDA(cudaMemsetAsync(scratch, 0, SCR_WORDS * sizeof(unsigned long long), s));
+  int g = grid_for(n, 256, di.sms);
+  count_models_kernel<<<g, 256, 0, s>>>(n, model_id, scratch);
+  g_launches++;
+  scatter_models_kernel<<<g, 256, 0, s>>>(n, model_id, scratch, perm, counters);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+
+  fx::SolveArgs a;
+  memset(&a, 0, sizeof a);
+  a.n = 0;
+  a.counts = scratch + SCR_COUNTS;
+  a.perm = perm;
+  a.params = params;
+  a.b = b;
+  a.i = i;
+  a.summary = summary;
+  a.counters = counters;
+  a.knots = k_max > 0 ? knots : nullptr;
+  a.k_max = k_max;
+  a.queue = scratch + SCR_QUEUES;
+  a.itol = o.itol;
+  a.rtol = o.rtol;
+  a.atol = o.atol;
+  a.ob = o.ob;
+  a.max_bisect = o.max_bisect;
+  a.max_ode_steps = o.max_ode_steps;
+  a.max_expansions = o.max_expansions;
+  a.radial_k = o.radial_k;
+
+  // fork: one persistent launch per model, side by side; empty buckets exit at once
+  FX_CUDA(cudaEventRecord(fk->begin, s));
+  for (int m = 0; m < FX_NUM_MODELS; m++) {
+    FX_CUDA(cudaStreamWaitEvent(fk->streams[m], fk->begin, 0));
+    a.slot = m;
+    const bool timing = g_kernel_timing.load() != 0;
+    if (timing) FX_CUDA(cudaEventRecord(fk->k0[m], fk->streams[m]));
+    if ((rc = launch_by_id(m, a, o.radial_k > 0, n, di.sms, fk->streams[m]))) return rc;
+    if (timing) FX_CUDA(cudaEventRecord(fk->k1[m], fk->streams[m]));
+    fk->timed[m] = timing;
+    FX_CUDA(cudaEventRecord(fk->done[m], fk->streams[m]));
+    FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
+  }
+  FX_CUDA(cudaFreeAsync(perm, s));
+  FX_CUDA(cudaFreeAsync(scratch, s));
+  return FX_OK;
+}
+
+int fx_solve_batch_host(int64_t n, const int32_t* model_id, const double* params, const double* b,
+                        const double* i, const fx_solve_options* opt, double* summary,
+                        int32_t* counters, int32_t k_max, double* knots) {
+  if (n < 0 || k_max < 0) return fail(FX_ERR_ARG, "negative size%s");
+  if (n == 0) return FX_OK;
+  if (!model_id || !params || !b || !i || !summary || !counters)
+    return fail(FX_ERR_ARG, "null pointer argument%s");
+  if (k_max > 0 && !knots) return fail(FX_ERR_ARG, "k_max > 0 needs a knots buffer%s");
+  cudaStream_t s = nullptr;
+  FX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  int32_t *d_model = nullptr, *d_cnt = nullptr;
+  double *d_par = nullptr, *d_b = nullptr, *d_i = nullptr, *d_sum = nullptr, *d_knots = nullptr;
+  size_t nn = (size_t)n;
+  int rc = FX_OK;
+  auto body = [&]() -> int {
+    FX_CUDA(cudaMallocAsync((void**)&d_model, nn * sizeof(int32_t), s));
+    FX_CUDA(cudaMallocAsync((void**)&d_par, nn * FX_NPARAM * sizeof(double), s));
+    FX_CUDA(cudaMallocAsync((void**)&d_b, nn * sizeof(double), s));
+    FX_CUDA(cudaMallocAsync((void**)&d_i, nn * sizeof(double), s));
+    FX_CUDA(cudaMallocAsync((void**)&d_sum, nn * FX_NSUM * sizeof(double), s));
+    FX_CUDA(cudaMallocAsync((void**)&d_cnt, nn * FX_NCNT * sizeof(int32_t), s));
+    if (k_max > 0) FX_CUDA(cudaMallocAsync((void**)&d_knots, nn * k_max * FX_KNOT * sizeof(double), s));
+    FX_CUDA(cudaMemcpyAsync(d_model, model_id, nn * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(d_par, params, nn * FX_NPARAM * sizeof(double), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(d_b, b, nn * sizeof(double), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemcpyAsync(d_i, i, nn * sizeof(double), cudaMemcpyHostToDevice, s));
+    FX_CUDA(cudaMemsetAsync(d_cnt, 0, nn * FX_NCNT * sizeof(int32_t), s));
+    int r = fx_solve_batch(n, d_model, d_par, d_b, d_i, opt, d_sum, d_cnt, k_max, d_knots, s);
+    if (r) return r;
+    FX_CUDA(cudaMemcpyAsync(summary, d_sum, nn * FX_NSUM * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaMemcpyAsync(counters, d_cnt, nn * FX_NCNT * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (k_max > 0)
+      FX_CUDA(cudaMemcpyAsync(knots, d_knots, nn * k_max * FX_KNOT * sizeof(double), cudaMemcpyDeviceToHost, s));
+    FX_CUDA(cudaStreamSynchronize(s));
+    return FX_OK;
+  };
+  rc = body();
+  void* bufs[] = {d_model, d_par, d_b, d_i, d_sum, d_cnt, d_knots};
+  for (void* p : bufs)
+    if (p) cudaFreeAsync(p, s);
+  cudaStreamSynchronize(s);
+  cudaStreamDestroy(s);
+  return rc;
+}
+
+int fx_eval_batch(int64_t n, const int32_t* counters, const double* knots, int32_t k_max, int64_t q,
+                  const double* o_query, int32_t per_problem, double* theta, double* dtheta_do,
+                  void* stream) {
+  if (n < 0 || q < 0 || k_max < 1) return fail(FX_ERR_ARG, "bad sizes%s");
+  if (n == 0 || q == 0) return FX_OK;
+  if (!counters || !knots || !o_query) return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  eval_kernel<<<grid_for(n * q, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      n, counters, knots, k_max, q, o_query, per_problem, theta, dtheta_do);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int fx_diffusivity_batch(int64_t n, const int32_t* model_id, const double* params, int64_t q,
+                         const double* theta, double* out, void* stream) {
+  if (n < 0 || q < 0) return fail(FX_ERR_ARG, "bad sizes%s");
+  if (n == 0 || q == 0) return FX_OK;
+  if (!model_id || !params || !theta || !out) return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  diffusivity_kernel<<<grid_for(n * q, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      n, model_id, params, q, theta, out);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int fx_inverse_batch(int64_t batch, int64_t npts, const double* o, const double* theta,
+                     double* D_at_knots, double* sorptivity, int32_t* status, double* do_dtheta,
+                     double* Iodtheta, void* stream) {
+  if (batch < 0 || npts < 0) return fail(FX_ERR_ARG, "bad sizes%s");
+  if (batch == 0) return FX_OK;
+  if (npts < 2) return fail(FX_ERR_ARG, "a profile needs at least 2 points%s");
+  if (!o || !theta || !D_at_knots || !sorptivity || !status)
+    return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  int launches = 0;
+  cudaError_t e = fx::inverse_launch(batch, npts, o, theta, D_at_knots, sorptivity, status,
+                                     do_dtheta, Iodtheta, di.sms, (cudaStream_t)stream, &launches);
+  g_launches += launches;
+  if (e != cudaSuccess) return fail(FX_ERR_CUDA, "inverse_launch: %s", cudaGetErrorString(e));
+  return FX_OK;
+}
+
+int fx_inverse_query_batch(int64_t batch, int64_t npts, const double* o, const double* theta,
+                           const double* do_dtheta, const double* Iodtheta, int64_t q,
+                           const double* theta_query, double* D_out, void* stream) {
+  if (batch < 0 || npts < 2 || q < 0) return fail(FX_ERR_ARG, "bad sizes%s");
+  if (batch == 0 || q == 0) return FX_OK;
+  if (!o || !theta || !do_dtheta || !Iodtheta || !theta_query || !D_out)
+    return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  fx::inverse_query_kernel<<<grid_for(batch * q, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      batch, npts, o, theta, do_dtheta, Iodtheta, q, theta_query, D_out);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int fx_pchip_eval_batch(int64_t batch, int64_t npts, const double* x, const double* y, int64_t q,
+                        const double* x_query, double* y_out, void* stream) {
+  if (batch < 0 || npts < 2 || q < 0) return fail(FX_ERR_ARG, "bad sizes%s");
+  if (batch == 0 || q == 0) return FX_OK;
+  if (!x || !y || !x_query || !y_out) return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  fx::pchip_eval_kernel<<<grid_for(batch * q, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      batch, npts, x, y, q, x_query, y_out);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int fx_measure_fp64_peak(double* flops_per_s, void* stream) {
+  if (!flops_per_s) return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  double* sink = nullptr;
+  FX_CUDA(cudaMallocAsync((void**)&sink, sizeof(double), s));
+  cudaEvent_t e0, e1;
+  FX_CUDA(cudaEventCreate(&e0));
+  FX_CUDA(cudaEventCreate(&e1));
+  const int block = 256, grid = di.sms * 8, iters = 4096;
+  dfma_peak_kernel<<<grid, block, 0, s>>>(sink, 64, 1.0);  // warm-up
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    FX_CUDA(cudaEventRecord(e0, s));
+    dfma_peak_kernel<<<grid, block, 0, s>>>(sink, iters, 1.0);
+    FX_CUDA(cudaEventRecord(e1, s));
+    FX_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    FX_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  g_launches += 6;
+  double flops = 2.0 * 64.0 * (double)iters * (double)block * (double)grid;
+  *flops_per_s = flops / ((double)best * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  FX_CUDA(cudaFreeAsync(sink, s));
+  return FX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+/*
+ * frontx_b200.h -- C ABI of libfrontx_b200.so: the B200 (sm_100a) batched
+ * Boltzmann-transformed shooting solve behind frontx.solve.
+ *
+ * The reference (gerlero/frontx 0.1.0) is pure Python on jax/diffrax and has
+ * no FFI of its own; its boundary for this path is the Python call
+ *     frontx.solve(D, *, b, i, itol=1e-3, max_steps=100, throw=True) -> Solution
+ *         (src/frontx/_forward.py:60-72)
+ * plus the Solution protocol (src/frontx/_forward.py:17-57,
+ * src/frontx/_boltzmann.py:101-161) and InterpolatedSolution
+ * (src/frontx/_inverse/interpolated.py:18-73).  An arbitrary Python callable D
+ * cannot cross a C ABI, so models are TAGGED: (model id, 12-double parameter
+ * block) -- the six families the north star names plus the two closed forms
+ * the reference's own tests use.  Each entry point below names the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA-runtime types in signatures
+ *     (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - `*_batch` entry points take DEVICE pointers owned by the caller and are
+ *     asynchronous on `stream`; nothing allocated by a call outlives it except
+ *     a small per-device work-queue counter block cached by the library;
+ *   - `*_host` entry points take HOST pointers, stage through device memory the
+ *     library owns, and return after the results are back in host memory;
+ *   - return 0 on success, negative on error; fx_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback: without a CUDA device every
+ *     compute entry point returns FX_ERR_CUDA.
+ */
+#ifndef FRONTX_B200_H
+#define FRONTX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FX_VERSION 100 /* 0.1.0 */
+
+#define FX_NPARAM 12 /* doubles per problem in `params` */
+#define FX_NSUM 8    /* doubles per problem in `summary` */
+#define FX_NCNT 8    /* int32 per problem in `counters` */
+#define FX_KNOT 4    /* doubles per dense-output knot: o, theta, dtheta/do, d2theta/do2 */
+
+/* Diffusivity models.  Parameter-block layouts (unused slots ignored):
+ *   FX_CONSTANT       {D0}                                   D = D0            (fronts.D.constant)
+ *   FX_POWER_LAW      {a, k, eps}                            D = a*theta^k+eps (fronts.D.power_law;
+ *                                                            tests/test_solve.py:151 D=theta)
+ *   FX_BROOKS_COREY   {n, l, Ks, alpha, theta_r, theta_s}    src/frontx/models.py:126-174
+ *   FX_VAN_GENUCHTEN  {n, m, l, Ks, alpha, theta_r, theta_s} src/frontx/models.py:177-253
+ *   FX_LETXS          {Lw, Ew, Tw, Ls, Es, Ts, Ks, alpha, theta_r, theta_s}  models.py:256-315
+ *   FX_LETD           {L, E, T, Dwt, theta_r, theta_s}       src/frontx/models.py:35-66
+ *   FX_LOG            {c0, c1}      D = c0 + c1*ln(theta)    tests/test_solve.py:40 (Philip 1960)
+ */
+enum fx_model {
+  FX_CONSTANT = 0,
+  FX_POWER_LAW = 1,
+  FX_BROOKS_COREY = 2,
+  FX_VAN_GENUCHTEN = 3,
+  FX_LETXS = 4,
+  FX_LETD = 5,
+  FX_LOG = 6,
+  FX_NUM_MODELS = 7
+};
+
+/* per-problem status in counters[.][0]; mirrors src/frontx/_forward.py:114-122:
+ * 0 -> RESULTS.successful, anything else -> RESULTS.max_steps_reached */
+enum fx_result {
+  FX_SUCCESSFUL = 0,
+  FX_MAX_STEPS_REACHED = 1, /* bisection used max_bisect steps without |residual| < itol */
+  FX_NO_BRACKET = 2         /* bracket expansion exhausted without a sign change          */
+};
+
+enum fx_error {
+  FX_OK = 0,
+  FX_ERR_ARG = -1,
+  FX_ERR_CUDA = -2,
+  FX_ERR_MODEL = -3
+};
+
+/* summary[j]  = {d_dob, oi, theta(oi), S0 = -2 D(b) d_dob, D(b), residual, lower, upper}
+ * counters[j] = {result, n_shots, n_expansions, n_attempts, n_rejected, n_rhs, n_jac, n_knots}
+ *   (n_attempts .. n_jac are summed over all shots; n_knots is the LAST shot's, which is the
+ *    one the reference returns as Solution -- _forward.py:109,115)                          */
+
+typedef struct fx_solve_options {
+  double itol;           /* 1e-3   _forward.py:69  */
+  int32_t max_bisect;    /* 100    _forward.py:70  */
+  int32_t max_ode_steps; /* 4096   diffrax.diffeqsolve default max_steps */
+  double rtol;           /* 1e-3   _forward.py:92  */
+  double atol;           /* 1e-6   _forward.py:92  */
+  int32_t max_expansions; /* 64    bound on Bisection(expand_if_necessary=True) */
+  int32_t radial_k;      /* 0 planar (the reference); 1 cylindrical/polar, 2 spherical */
+  double ob;             /* 0 for the reference; >0 only with radial_k>0 */
+} fx_solve_options;
+
+void fx_default_solve_options(fx_solve_options *opt);
+
+/* Replaces frontx.solve (src/frontx/_forward.py:60-122) for a batch of n
+ * independent problems: Kvaerno5 ESDIRK shots (diffrax, :84-95) with the boolean
+ * event (:76-78), bisection on d_dob (:104-112).  One GPU thread owns one
+ * problem.  k_max = 0 skips dense output; otherwise knots is [n][k_max][4] and
+ * rows hold the last shot's accepted steps (n_knots may exceed k_max: the table
+ * is then truncated and Solution evaluation refuses it).  All pointers device. */
+int fx_solve_batch(int64_t n, const int32_t *model_id, const double *params /*[n][12]*/,
+                   const double *b /*[n]*/, const double *i /*[n]*/,
+                   const fx_solve_options *opt /*host; NULL = defaults*/,
+                   double *summary /*[n][8]*/, int32_t *counters /*[n][8]*/,
+                   int32_t k_max, double *knots /*[n][k_max][4] or NULL*/, void *stream);
+
+/* Same, HOST pointers in and out (H2D, kernel, D2H inside the call). */
+int fx_solve_batch_host(int64_t n, const int32_t *model_id, const double *params,
+                        const double *b, const double *i, const fx_solve_options *opt,
+                        double *summary, int32_t *counters, int32_t k_max, double *knots);
+
+/* Replaces Solution.__call__ / Solution.d_do (src/frontx/_forward.py:25-37):
+ * clip o to [0, oi], locate the step, cubic Hermite dense output.  o_query is
+ * [n][q] (per_problem=1) or [q] shared by all problems (per_problem=0).
+ * theta / dtheta_do are [n][q]; either may be NULL.  All pointers device. */
+int fx_eval_batch(int64_t n, const int32_t *counters /*[n][8]*/, const double *knots, int32_t k_max,
+                  int64_t q, const double *o_query, int32_t per_problem, double *theta,
+                  double *dtheta_do, void *stream);
+
+/* D, dD/dtheta, d2D/dtheta2 at arbitrary theta (the callable the reference keeps
+ * as Solution.D and uses in flux/sorptivity, src/frontx/_boltzmann.py:151-161).
+ * theta is [n][q]; out is [n][q][3]. All pointers device. */
+int fx_diffusivity_batch(int64_t n, const int32_t *model_id, const double *params, int64_t q,
+                         const double *theta, double *out, void *stream);
+
+/* Replaces InterpolatedSolution(o, theta) (src/frontx/_inverse/interpolated.py:18-73)
+ * for `batch` profiles of `npts` points each, theta strictly monotone in o:
+ *   D_at_knots [batch][npts]  InterpolatedSolution.D at every data point, caller's order  (:59-67)
+ *   sorptivity [batch][4]     {PCHIP Int theta do over the data (:69-73), trapezoid Int theta do
+ *                              (_inverse/sorptivity.py:16-19), PCHIP-extrapolated Int_0^o[0], 0}
+ *   status     [batch]        0 ok, 1 theta not strictly monotone (D is then meaningless)
+ *   do_dtheta, Iodtheta [batch][npts], optional (NULL to skip): the inverse PCHIP's knot
+ *                              slopes and antiderivative values (minus its value at theta=i),
+ *                              which fx_inverse_query_batch needs.
+ * All pointers device; asynchronous on stream. */
+int fx_inverse_batch(int64_t batch, int64_t npts, const double *o, const double *theta,
+                     double *D_at_knots, double *sorptivity, int32_t *status,
+                     double *do_dtheta, double *Iodtheta, void *stream);
+
+/* InterpolatedSolution.D at arbitrary theta (interpolated.py:59-67): interval search in the
+ * profile's theta, cubic pieces of derivative() and antiderivative(); NaN outside the data
+ * range (extrapolate=False, :47).  theta_query / D_out are [batch][q].  Device pointers. */
+int fx_inverse_query_batch(int64_t batch, int64_t npts, const double *o, const double *theta,
+                           const double *do_dtheta, const double *Iodtheta, int64_t q,
+                           const double *theta_query, double *D_out, void *stream);
+
+/* InterpolatedSolution.__call__ (interpolated.py:30,52-57): the forward PCHIP y(x) (x = o
+ * strictly ascending, y = theta) at arbitrary x_query[batch][q], end polynomials
+ * extrapolated (PchipInterpolator default). Device pointers. */
+int fx_pchip_eval_batch(int64_t batch, int64_t npts, const double *x, const double *y, int64_t q,
+                        const double *x_query, double *y_out, void *stream);
+
+/* measured FP64 FMA throughput of the current device, FLOP/s (roofline denominator) */
+int fx_measure_fp64_peak(double *flops_per_s, void *stream);
+
+/* Kernel timing for the roofline: when on, fx_solve_batch brackets each per-model
+ * shoot_bisect_kernel launch with CUDA events on the stream it runs on;
+ * fx_last_solve_kernel_ms waits for and returns the last such duration. */
+void fx_set_kernel_timing(int on);
+int fx_last_solve_kernel_ms(int model, float *ms);
+
+/* number of kernel launches issued by this library in this process so far */
+int64_t fx_launch_count(void);
+
+const char *fx_last_error(void);
+int fx_version(void);
+int fx_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -81,6 +81,9 @@ static jet Se_of(double theta, double theta_r, double theta_s) {
   return r;
 }
 
+static int g_vg_literal = 0;
+void fxo_set_vg_literal(int on) { g_vg_literal = on; }
+
 /* D(theta) as a jet, from the reference definitions */
 static jet D_jet(int model, const double *p, double theta) {
   jet th = {theta, 1.0, 0.0, 0.0};
@@ -111,8 +114,16 @@ static jet D_jet(int model, const double *p, double theta) {
       double n = p[0], m = p[1], l = p[2], Ks = p[3], alpha = p[4];
       jet Se = Se_of(theta, p[5], p[6]);
       jet u = j_powc(Se, 1.0 / m);
-      jet h = j_scale(-1.0 / alpha, j_powc(j_sub(j_recip(u), one), 1.0 / n));
-      jet w = j_sub(one, j_powc(j_sub(one, u), m));
+      /* 1 - Se^(1/m) has condition number ~1e7 at the reference's own test point
+       * b = theta_s - 1e-7: the literal subtraction carries ~1e-9 relative rounding noise that
+       * differs between pow() implementations (glibc, XLA, CUDA) and that the shooting
+       * problem amplifies ~1e4-fold.  By default the VALUE of (1 - u) is formed without
+       * cancellation, -expm1(log(Se)/m); every other term is the literal expression.
+       * fxo_set_vg_literal(1) restores the literal subtraction (tests measure the gap). */
+      jet omu = j_sub(one, u);
+      if (!g_vg_literal) omu.v = -expm1(log(Se.v) / m);
+      jet h = j_scale(-1.0 / alpha, j_powc(g_vg_literal ? j_sub(j_recip(u), one) : j_div(omu, u), 1.0 / n));
+      jet w = j_sub(one, j_powc(omu, m));
       jet kr = j_mul(j_powc(Se, l), j_mul(w, w));
       jet C = j_recip(j_deriv(h));
       return j_div(j_scale(Ks, kr), C);

@@ -66,6 +66,10 @@ typedef struct {
 
 void fxo_default_options(fxo_options *opt);
 
+/* van Genuchten only: 1 = form 1 - Se^(1/m) by the literal (cancelling) subtraction,
+ * 0 (default) = cancellation-free value; see the comment in D_jet(). Process-global. */
+void fxo_set_vg_literal(int on);
+
 /* D, D', D'' from the reference DEFINITIONS by 3rd-order Taylor jets. out[3]. */
 void fxo_D(int model, const double *p, double theta, double *out);
 
@@ -87,14 +91,6 @@ int fxo_solve_batch(int64_t n, const int32_t *model, const double *params,
                     const double *b, const double *i, double itol, int max_bisect,
                     const fxo_options *opt, double *summary, int32_t *counters,
                     int k_max, double *knots, int nthreads);
-
-/* flow-rate boundary (north star C4; no reference code -- fronts semantics):
- * bisect on the boundary value b so that the far field meets i, with
- * d_dob = -Qb/(D(b)*angle*ob*height). */
-int fxo_solve_flowrate(int model, const double *p, double Qb, double i, double itol,
-                       int max_bisect, const fxo_options *opt, double angle, double height,
-                       double b_lo, double b_hi,
-                       double *summary, int32_t *counters, int k_max, double *knots);
 
 /* dense output (Solution.__call__/d_do, _forward.py:25-37): clip, searchsorted, Hermite */
 void fxo_eval(int n_knots, const double *knots, int64_t q, const double *o,

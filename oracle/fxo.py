@@ -168,5 +168,10 @@ def inverse(o, theta):
     return rc, Dk, s1.value, s2.value
 
 
+def set_vg_literal(on: bool) -> None:
+    """van Genuchten: literal cancelling subtraction (True) or cancellation-free value (False, default)."""
+    lib().fxo_set_vg_literal(int(bool(on)))
+
+
 def num_threads() -> int:
     return int(lib().fxo_num_threads())

@@ -1,0 +1,87 @@
+"""Shared fixtures.  Tests marked ``gpu`` need a B200; everything else runs on CPU.
+
+The CPU oracle (oracle/) is test infrastructure: it is the checker here, never
+the thing under test in the ``gpu`` tests, and the product package never
+imports it.
+"""
+
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+# boundary values of the reference's forward tests (tests/test_solve.py:127-128)
+B_PAPER = 0.7 - 1e-7
+I_PAPER = 0.025
+
+
+def paper_models():
+    """The six parameter sets of /root/reference/tests/test_solve.py:47-113."""
+    from frontx_b200 import models as M
+
+    return {
+        "LETd#1": M.LETd(L=0.004569, E=12930, T=1.505, Dwt=4.660e-4, theta_range=(0.019852, 0.7)),
+        "LETd#2": M.LETd(Dwt=1.004e-3, L=1.356, E=10010, T=1.224, theta_range=(0.00625, 0.7)),
+        "VG(n)": M.VanGenuchten(n=8.093, l=2.344, Ks=2.079e-6, theta_range=(0.004943, 0.7)),
+        "VG(m)": M.VanGenuchten(m=0.8861, l=2.331, Ks=2.105e-6, theta_range=(0.005623, 0.7)),
+        "BC": M.BrooksAndCorey(n=0.2837, l=4.795, Ks=3.983e-6, theta_range=(2.378e-5, 0.7)),
+        "LETxs": M.LETxs(Lw=1.651, Ew=230.5, Tw=0.9115, Ls=0.517, Es=493.6, Ts=0.3806, Ks=8.900e-3,
+                         theta_range=(0.01176, 0.7)),
+    }
+
+
+@pytest.fixture(scope="session")
+def paper():
+    return paper_models()
+
+
+@pytest.fixture(scope="session")
+def fxo():
+    from oracle import fxo as _fxo
+
+    _fxo.build()
+    return _fxo
+
+
+def vg_sweep(n: int, seed: int = 0):
+    """BASELINE config C2: van Genuchten sweep."""
+    from frontx_b200 import models as M
+
+    rng = np.random.default_rng(seed)
+    nn = rng.uniform(1.5, 9.0, n)
+    alpha = np.exp(rng.uniform(np.log(0.5), np.log(5.0), n))
+    Ks = np.exp(rng.uniform(np.log(1e-7), np.log(1e-4), n))
+    return M.VanGenuchten.batch(n=nn, alpha=alpha, Ks=Ks, l=0.5, theta_range=(0.005, 0.7))
+
+
+def mixed_sweep(n: int, seed: int = 1):
+    """BASELINE config C3: Brooks-Corey (even k) / LETd (odd k), interleaved."""
+    from frontx_b200 import ModelBatch
+    from frontx_b200 import models as M
+
+    rng = np.random.default_rng(seed)
+    nb = (n + 1) // 2
+    nl = n // 2
+    bc = M.BrooksAndCorey.batch(n=rng.uniform(0.2, 0.6, nb), l=rng.uniform(1.0, 5.0, nb),
+                                Ks=np.exp(rng.uniform(np.log(1e-6), np.log(1e-5), nb)),
+                                theta_range=(2.378e-5, 0.7))
+    ld = M.LETd.batch(L=rng.uniform(0.004, 1.5, nl), E=np.exp(rng.uniform(np.log(1e3), np.log(2e4), nl)),
+                      T=rng.uniform(1.0, 1.6, nl), Dwt=np.exp(rng.uniform(np.log(1e-4), np.log(2e-3), nl)),
+                      theta_range=(0.0198, 0.7))
+    ids = np.empty(n, dtype=np.int32)
+    par = np.empty((n, 12))
+    ids[0::2], par[0::2] = bc.model_id, bc.params
+    ids[1::2], par[1::2] = ld.model_id, ld.params
+    return ModelBatch(ids, par)

@@ -1,0 +1,373 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle, on a B200.
+
+Tolerances are the north star's: theta profiles and sorptivity within 1e-6
+relative, the inverse within 1e-9, shooting iteration counts equal.  The
+oracle is the checker only; everything under test goes through
+libfrontx_b200.so.
+"""
+
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+from conftest import B_PAPER, I_PAPER, mixed_sweep, paper_models, vg_sweep
+
+import frontx_b200 as fx
+from frontx_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = json.loads((Path(__file__).parent / "golden" / "diffusivity_golden.json").read_text())
+CNT = ("result", "n_shots", "n_expansions", "n_attempts", "n_rejected", "n_rhs", "n_jac", "n_knots")
+
+
+def counters_of(cpu: dict) -> np.ndarray:
+    return np.stack([cpu[k] for k in CNT], axis=1)
+
+
+# ---------------------------------------------------------------------------
+# diffusivity models
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(GOLDEN["sets"]))
+def test_diffusivity_vs_golden(paper, name):
+    m = paper[name]
+    for pname, row in GOLDEN["sets"][name]["values"].items():
+        got = m.derivatives(np.array([row["theta"]]))[0]
+        want = np.array([float(row["D"]), float(row["D1"]), float(row["D2"])])
+        rtol = 3e-9 if pname.startswith("b=") else 5e-12
+        np.testing.assert_allclose(got, want, rtol=rtol, err_msg=f"{name} @ {pname}")
+
+
+def test_diffusivity_vs_oracle_dense(fxo, paper):
+    """Closed-form kernels vs the oracle's autodiff-style jets over the whole domain."""
+    for name, m in paper.items():
+        tr, ts = m.theta_range
+        th = tr + (ts - tr) * np.concatenate([np.geomspace(1e-4, 0.5, 40), 1 - np.geomspace(2e-7, 0.5, 40)])
+        got = m.derivatives(th)
+        want = fxo.D(m.model_id, m.params(), th)
+        np.testing.assert_allclose(got, want, rtol=2e-11, err_msg=name)
+    for m, th in ((fx.D.power_law(k=4), np.linspace(0.05, 1.2, 30)),
+                  (fx.D.power_law(k=2.5, a=3.0, epsilon=0.1), np.linspace(0.05, 1.2, 30)),
+                  (fx.D.philip_exact(), np.linspace(1e-6, 1.0, 30)), (fx.D.constant(2.5), np.linspace(0, 1, 5))):
+        np.testing.assert_allclose(m.derivatives(th), fxo.D(m.model_id, m.params(), th), rtol=1e-13, atol=1e-300)
+
+
+def test_diffusivity_outside_domain_is_nan(paper):
+    m = paper["VG(n)"]
+    out = m.derivatives(np.array([m.theta_range[0] - 1e-3, m.theta_range[1] + 1e-3]))
+    assert np.isnan(out[:, 0]).all()
+
+
+# ---------------------------------------------------------------------------
+# forward solve: the six paper sets + the closed-form cases (rows a1-a4, a6-a8)
+# ---------------------------------------------------------------------------
+def reference_cases():
+    ms = paper_models()
+    cases = [(k, m, B_PAPER, I_PAPER) for k, m in ms.items()]
+    cases.append(("power_law k=4 (C1)", fx.D.power_law(k=4), 1.0, 0.1))
+    cases.append(("philip", fx.D.philip_exact(), 1.0, 0.0))
+    cases.append(("constant", fx.D.constant(1.0), 1.0, 0.0))
+    cases.append(("wetting front reversed (i>b)", ms["LETd#2"], 0.1, 0.6))
+    return cases
+
+
+@pytest.fixture(scope="module")
+def solved_cases(fxo):
+    cases = reference_cases()
+    models = fx.ModelBatch.from_models([c[1] for c in cases])
+    b = np.array([c[2] for c in cases])
+    i = np.array([c[3] for c in cases])
+    gpu = fx.solve_batch(models, b=b, i=i, k_max=512, throw=False)
+    ref = fxo.solve_batch(models.model_id, models.params, b, i, k_max=512)
+    return cases, gpu, ref
+
+
+def test_paper_sets_counters_identical(solved_cases):
+    cases, gpu, ref = solved_cases
+    got = counters_of(gpu.cpu())
+    for j, c in enumerate(cases):
+        assert got[j].tolist() == ref["counters"][j].tolist(), c[0]
+
+
+def test_paper_sets_summary(solved_cases):
+    cases, gpu, ref = solved_cases
+    g = gpu.cpu()
+    s = ref["summary"]
+    np.testing.assert_allclose(g["d_dob"], s[:, 0], rtol=1e-13)  # same bisection midpoints
+    np.testing.assert_allclose(g["oi"], s[:, 1], rtol=1e-6)
+    np.testing.assert_allclose(g["i"], s[:, 2], rtol=1e-6)
+    np.testing.assert_allclose(g["sorptivity"], s[:, 3], rtol=1e-6)
+    np.testing.assert_allclose(g["D_b"], s[:, 4], rtol=1e-11)
+    np.testing.assert_allclose(g["residual"], s[:, 5], rtol=1e-4, atol=1e-9)
+
+
+def test_paper_sets_profiles(fxo, solved_cases):
+    cases, gpu, ref = solved_cases
+    for j, c in enumerate(cases):
+        nk = int(ref["counters"][j, 7])
+        o = np.linspace(0, ref["summary"][j, 1], 300)
+        th_c, dth_c = fxo.evaluate(ref["knots"][j, :nk], o)
+        sol = gpu[j]
+        np.testing.assert_allclose(sol(o), th_c, rtol=1e-6, err_msg=c[0])
+        np.testing.assert_allclose(sol.d_do(o), dth_c, rtol=1e-5, atol=1e-6 * np.abs(dth_c).max(), err_msg=c[0])
+        # sorptivity along the profile: -2 D(theta) dtheta/do  (_boltzmann.py:158-161)
+        S_c = -2 * fxo.D(c[1].model_id, c[1].params(), th_c)[:, 0] * dth_c
+        np.testing.assert_allclose(sol.sorptivity(o), S_c, rtol=1e-5, atol=1e-6 * np.abs(S_c).max(), err_msg=c[0])
+
+
+def test_reference_test_exact():
+    """/root/reference/tests/test_solve.py:38-42 through the public API."""
+    theta = fx.solve(D=fx.D.philip_exact(), i=0, b=1)
+    o = np.linspace(0, 20, 100)
+    assert theta(o) == pytest.approx(np.exp(-o), abs=1e-3)
+    assert theta.result == fx.RESULTS.successful
+    assert theta.b == 1.0 and theta.d_dob == pytest.approx(-1.0, abs=1e-3)
+    assert theta(theta.oi) == pytest.approx(theta.i)
+
+
+def test_reference_test_unsolvable():
+    """/root/reference/tests/test_solve.py:148-156."""
+    with pytest.raises(fx.SolveError):
+        fx.solve(D=fx.D.power_law(k=1), i=-1, b=1)
+    assert fx.solve(D=fx.D.power_law(k=1), i=-1, b=1, throw=False).result != fx.RESULTS.successful
+
+
+@pytest.mark.parametrize("name", list(paper_models()))
+def test_reference_test_fronts_papers(fxo, paper, name):
+    """/root/reference/tests/test_solve.py:116-145 with the oracle in place of `fronts`."""
+    D = paper[name]
+    sol = fx.solve(D, b=B_PAPER, i=I_PAPER)
+    ref = fxo.solve(D.model_id, D.params(), B_PAPER, I_PAPER)
+    o = np.linspace(0, ref["summary"][1], 100)
+    assert sol(o) == pytest.approx(fxo.evaluate(ref["knots"], o)[0], abs=5e-2)
+    assert D(0.5) == pytest.approx(fxo.D(D.model_id, D.params(), [0.5])[0, 0])
+    # Solution algebra (_boltzmann.py:137-161)
+    r, t = 1e-3, 4.0
+    assert sol(r, t) == pytest.approx(sol(o=r / 2.0))
+    assert sol.d_dr(r, t) == pytest.approx(sol.d_do(r / 2.0) / 2.0)
+    assert sol.flux(r, t) == pytest.approx(-D(sol(r, t)) * sol.d_dr(r, t))
+    assert sol.sorptivity() == pytest.approx(-2 * D(B_PAPER) * sol.d_dob)
+    assert sol.n_shots == ref["counters"][1]
+
+
+# ---------------------------------------------------------------------------
+# sweeps: BASELINE configs C2 and C3 at oracle-sized batches
+# ---------------------------------------------------------------------------
+def compare_sweep(fxo, models, n_expected_models):
+    gpu = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    ref = fxo.solve_batch(models.model_id, models.params, B_PAPER, I_PAPER)
+    g = gpu.cpu()
+    got = counters_of(g)
+    same = (got == ref["counters"]).all(axis=1)
+    ok = ref["counters"][:, 0] == 0
+    s = ref["summary"]
+    rel_d = np.abs(g["d_dob"] / s[:, 0] - 1)
+    rel_S = np.abs(g["sorptivity"] / s[:, 3] - 1)
+    rel_i = np.abs(g["i"] / s[:, 2] - 1)
+    rel_oi = np.abs(g["oi"] / s[:, 1] - 1)
+    within = (rel_d < 1e-6) & (rel_S < 1e-6) & (rel_i < 1e-6) & (rel_oi < 1e-6)
+    return {"same": same, "ok": ok, "within": within, "shots_equal": got[:, 1] == ref["counters"][:, 1],
+            "result_equal": got[:, 0] == ref["counters"][:, 0], "gpu": g, "ref": ref}
+
+
+def test_vg_sweep_parity(fxo):
+    """C2 at N=3000: a decision flip (accept/reject, chord convergence) moves a profile by
+    O(1e-5); the fraction of problems with ANY differing counter is reported and bounded."""
+    r = compare_sweep(fxo, vg_sweep(3000), 1)
+    frac_same, frac_within = r["same"].mean(), r["within"].mean()
+    print(f"\nVG sweep: identical decision counters {frac_same:.4f}, within 1e-6 {frac_within:.4f}, "
+          f"same status {r['result_equal'].mean():.4f}, same shots {r['shots_equal'].mean():.4f}")
+    assert r["within"][r["same"]].all()  # no flip  =>  1e-6 parity, always
+    assert frac_same >= 0.97
+    assert frac_within >= 0.97
+    assert r["result_equal"].mean() >= 0.995
+    assert (r["gpu"]["n_expansions"] == 0).all()
+
+
+def test_mixed_sweep_parity(fxo):
+    """C3 at N=3000: Brooks-Corey / LETd interleaved, bucketed by model on the device."""
+    models = mixed_sweep(3000)
+    r = compare_sweep(fxo, models, 2)
+    print(f"\nmixed sweep: identical decision counters {r['same'].mean():.4f}, within 1e-6 {r['within'].mean():.4f}")
+    assert r["within"][r["same"]].all()
+    assert r["same"].mean() >= 0.97
+    assert r["result_equal"].mean() >= 0.995
+
+
+# ---------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------
+def test_empty_and_single():
+    empty = fx.solve_batch(fx.ModelBatch(np.zeros(0, np.int32), np.zeros((0, 12))), b=1.0, i=0.1, k_max=4)
+    assert len(empty) == 0
+    one = fx.solve_batch(fx.D.power_law(k=4), b=1.0, i=0.1, k_max=0)
+    assert len(one) == 1 and one.knots is None
+    with pytest.raises(fx.FrontxB200Error):
+        one.evaluate([0.0])
+
+
+def test_invalid_model_id_is_flagged():
+    good = fx.D.power_law(k=4).params()
+    mb = fx.ModelBatch(np.array([1, 99, 1], dtype=np.int32), np.stack([good, good, good]))
+    sol = fx.solve_batch(mb, b=1.0, i=0.1, k_max=0, throw=False)
+    assert sol.counters[:, 0].tolist() == [0, -1, 0]
+    with pytest.raises(fx.SolveError):
+        sol.raise_for_status()
+
+
+def test_knot_table_truncation_is_detected(paper):
+    sol = fx.solve_batch(paper["BC"], b=B_PAPER, i=I_PAPER, k_max=32, throw=False)
+    assert int(sol.counters[0, 7]) > 32
+    with pytest.raises(fx.SolveError, match="k_max"):
+        sol.raise_for_status()
+    assert np.isnan(sol.theta([0.0]).cpu().numpy()).all()
+    full = fx.solve(paper["BC"], b=B_PAPER, i=I_PAPER)  # solve() grows the table by itself
+    assert np.isfinite(full(np.linspace(0, full.oi, 50))).all()
+
+
+def test_b_equals_i_terminates():
+    sol = fx.solve_batch(fx.D.constant(1.0), b=0.5, i=0.5, k_max=8, throw=False)
+    assert np.isfinite(sol.summary.cpu().numpy()).all()
+
+
+def test_eval_clipping_and_per_problem_queries(fxo, paper):
+    models = fx.ModelBatch.from_models([paper["LETd#1"], paper["LETxs"]])
+    sol = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=256)
+    oi = sol.oi.cpu().numpy()
+    q = np.stack([np.linspace(-0.1 * x, 1.5 * x, 64) for x in oi])
+    th, dth = sol.evaluate(q)
+    th = th.cpu().numpy()
+    assert np.all(th[:, 0] == B_PAPER)  # clipped to o=0
+    np.testing.assert_allclose(th[:, -1], sol.i.cpu().numpy(), rtol=1e-14)  # clipped to oi
+    shared = sol.theta(np.linspace(0, oi.min(), 16)).cpu().numpy()
+    assert shared.shape == (2, 16)
+
+
+def test_host_entry_point_matches_device_entry_point(paper):
+    models = vg_sweep(512, seed=5)
+    dev = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=16, throw=False)
+    summary, counters, knots = fx.solve_batch_host(models, B_PAPER, I_PAPER, k_max=16)
+    np.testing.assert_array_equal(summary, dev.summary.cpu().numpy())
+    np.testing.assert_array_equal(counters, dev.counters.cpu().numpy())
+    np.testing.assert_array_equal(knots, dev.knots.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------
+# full-size properties (BASELINE sizes; no oracle needed)
+# ---------------------------------------------------------------------------
+def test_full_size_properties_c2():
+    n = 100_000
+    models = vg_sweep(n)
+    a = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    g = a.cpu()
+    ok = g["result"] == 0
+    assert ok.mean() > 0.99
+    assert np.all(np.abs(g["i"][ok] - I_PAPER) < 1e-3)  # far field met within itol
+    assert np.all(np.abs(g["residual"][ok]) < 1e-3)
+    np.testing.assert_allclose(g["sorptivity"], -2 * g["D_b"] * g["d_dob"], rtol=1e-15)
+    assert np.all(g["d_dob"] < 0) and np.all(g["oi"] > 0)
+    assert np.all(g["n_jac"] == g["n_attempts"]) and np.all(g["n_rhs"] > 10 * g["n_attempts"])
+    assert np.all(g["n_expansions"] == 0)
+    # run-to-run determinism and independence from batch order / neighbours
+    perm = np.random.default_rng(1).permutation(n)
+    b2 = fx.solve_batch(models[perm], b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    np.testing.assert_array_equal(b2.summary.cpu().numpy(), a.summary.cpu().numpy()[perm])
+    np.testing.assert_array_equal(b2.counters.cpu().numpy(), a.counters.cpu().numpy()[perm])
+    # alpha and Ks only rescale D: sorptivity^2 / (Ks/alpha) depends on n alone up to atol effects
+    print(f"\nC2 full size: success {ok.mean():.4f}, shots mean {g['n_shots'].mean():.2f} "
+          f"(min {g['n_shots'].min()}, max {g['n_shots'].max()}), attempts mean {g['n_attempts'].mean():.0f}")
+
+
+# ---------------------------------------------------------------------------
+# inverse path (row a9): parity within 1e-9
+# ---------------------------------------------------------------------------
+def inverse_profiles():
+    rng = np.random.default_rng(3)
+    o = np.linspace(0, 20, 100)
+    yield "exp100", o, np.exp(-o)
+    o2 = np.sort(rng.uniform(0, 12, 1500))
+    o2[0] = 0.0
+    yield "ragged (2 tiles)", o2, 0.1 + 0.8 * np.exp(-1.7 * o2)
+    o3 = np.linspace(0.5, 9, 40)
+    yield "offset", o3, 1.0 / (1.0 + o3) ** 2
+    o4 = np.linspace(0, 3, 33)
+    yield "increasing", o4, 0.2 + 0.5 * np.tanh(o4)
+    yield "three", np.array([0.0, 1.0, 2.5]), np.array([1.0, 0.4, 0.1])
+    yield "two", np.array([0.0, 2.0]), np.array([1.0, 0.25])
+    o5 = np.linspace(0, 20 / 1.3, 20_000)
+    yield "C5-like 20k", o5, np.exp(-1.3 * o5)
+    yield "tile boundary 1024", np.linspace(0, 5, 1024), np.exp(-np.linspace(0, 5, 1024))
+    yield "tile boundary 1025", np.linspace(0, 5, 1025), np.exp(-np.linspace(0, 5, 1025))
+    yield "tile boundary 2049", np.linspace(0, 5, 2049), np.exp(-np.linspace(0, 5, 2049))
+
+
+@pytest.mark.parametrize("case", list(inverse_profiles()), ids=lambda c: c[0])
+def test_inverse_parity(fxo, case):
+    _, o, th = case
+    rc, D_c, s_pchip, s_trapz = fxo.inverse(o, th)
+    res = fx.inverse(o, th)
+    D_g = res.D_at_knots[0].cpu().numpy()
+    np.testing.assert_allclose(D_g, D_c, rtol=1e-9, atol=1e-12 * np.abs(D_c).max())
+    assert float(res.sorptivity()[0]) == pytest.approx(s_pchip, rel=1e-9)
+    assert float(res._sorp[0, 1]) == pytest.approx(s_trapz, rel=1e-12)
+    assert int(res.status[0]) == 0
+
+
+def test_inverse_batched_equals_single(fxo):
+    rng = np.random.default_rng(4)
+    a = rng.uniform(0.5, 2.0, 7)
+    o = np.stack([np.linspace(0, 20 / x, 3000) for x in a])
+    th = np.exp(-a[:, None] * o)
+    res = fx.inverse(o, th)
+    D = res.D_at_knots.cpu().numpy()
+    for j in range(len(a)):
+        rc, D_c, s_pchip, _ = fxo.inverse(o[j], th[j])
+        np.testing.assert_allclose(D[j], D_c, rtol=1e-9, atol=1e-12 * np.abs(D_c).max())
+        # analytic: D = (1 - ln theta)/(2 a^2)
+        sel = th[j] > 1e-6
+        assert np.abs(D[j][sel] * a[j] ** 2 - 0.5 * (1 - np.log(th[j][sel]))).max() < 1e-3
+    again = fx.inverse(o, th).D_at_knots.cpu().numpy()
+    np.testing.assert_array_equal(D, again)  # bit-reproducible scan
+
+
+def test_reference_test_inverse():
+    """/root/reference/tests/test_inverse.py:29-39,51-62 through the public API."""
+    o = np.linspace(0, 20, 100)
+    sol = fx.InterpolatedSolution(o, np.exp(-o))
+    assert sol(o) == pytest.approx(np.exp(-o))
+    theta = np.linspace(1e-6, 1, 100)
+    assert sol.D(theta) == pytest.approx(0.5 * (1 - np.log(theta)), abs=5e-2)
+    assert sol.sorptivity() == pytest.approx(1, abs=1e-4)
+    o5 = np.linspace(0, 20, 500)
+    assert fx.sorptivity(o5, np.exp(-o5), b=1, i=0) == pytest.approx(1, abs=1e-3)
+    assert np.isnan(sol.D(1.5))  # extrapolate=False (interpolated.py:47)
+
+
+def test_inverse_query_vs_scipy_twin():
+    from test_oracle_inverse import scipy_twin
+
+    o = np.linspace(0, 10, 400)
+    th = 0.05 + 0.9 * np.exp(-0.8 * o)
+    D, _ = scipy_twin(o, th)
+    tq = np.linspace(th.min(), th.max(), 777)
+    got = fx.InterpolatedSolution(o, th).D(tq)
+    want = D(tq)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())
+
+
+def test_inverse_rejects_non_monotone():
+    o = np.linspace(0, 5, 64)
+    th = np.exp(-o)
+    th[30] = th[29]
+    with pytest.raises(ValueError, match="monotone"):
+        fx.inverse(o, th)
+    assert int(fx.inverse(o, th, throw=False).status[0]) == 1
+
+
+def test_launch_counter_moves():
+    before = _lib.launch_count()
+    fx.solve_batch(fx.D.power_law(k=4), b=1.0, i=0.1, k_max=0)
+    assert _lib.launch_count() >= before + 3
