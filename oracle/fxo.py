@@ -35,13 +35,78 @@ class Options(C.Structure):
 
 
 def build(force: bool = False) -> Path:
-    srcs = [HERE / "fx_oracle.c", HERE / "fx_oracle_inverse.c", HERE / "fx_oracle.h"]
-    stale = (not LIB.exists()) or any(s.stat().st_mtime > LIB.stat().st_mtime for s in srcs)
-    if force or stale:
+    csrc = HERE.parent / "frontx_b200" / "csrc"
+    srcs = [HERE / "fx_oracle.c", HERE / "fx_oracle_inverse.c", HERE / "fx_oracle.h", HERE / "fx_twin.cpp",
+            HERE / "Makefile", csrc / "fx_math.cuh", csrc / "fx_models.cuh", csrc / "fx_arith.cuh"]
+    libs = [LIB, HERE / "libfx_twin.so", HERE / "libfx_twin_fma.so"]
+    stale = any(not p.exists() for p in libs) or any(
+        s.stat().st_mtime > min(p.stat().st_mtime for p in libs) for s in srcs if s.exists())
+    missing_sources = not all(s.exists() for s in srcs)
+    if (force or stale) and not missing_sources:
         env = dict(os.environ)
         env.pop("CC", None)
-        subprocess.run(["make", "-C", str(HERE), "-B"], check=True, env=env, capture_output=True)
+        env.pop("CXX", None)
+        proc = subprocess.run(["make", "-C", str(HERE), "-B"], env=env, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("building the oracle failed:\n" + proc.stdout + proc.stderr)
     return LIB
+
+
+_twin = None
+
+
+def twin() -> C.CDLL:
+    """Host build of the kernel's arithmetic under plain loops (oracle/fx_twin.cpp)."""
+    global _twin
+    if _twin is None:
+        build()
+        has_fma = False
+        try:
+            has_fma = " fma " in open("/proc/cpuinfo").read().replace("\n", " ")
+        except OSError:
+            pass
+        L = C.CDLL(str(HERE / ("libfx_twin_fma.so" if has_fma else "libfx_twin.so")))
+        dp = C.POINTER(C.c_double)
+        ip = C.POINTER(C.c_int32)
+        L.fxt_D.argtypes = [C.c_int, dp, C.c_double, dp]
+        for name in ("fxt_log", "fxt_exp", "fxt_expm1"):
+            getattr(L, name).argtypes = [C.c_double]
+            getattr(L, name).restype = C.c_double
+        L.fxt_solve_batch.argtypes = [C.c_int64, ip, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double,
+                                      C.c_double, C.c_int, C.c_int, C.c_double, dp, ip, C.c_int, dp, C.c_int]
+        L.fxt_solve_batch.restype = C.c_int
+        _twin = L
+    return _twin
+
+
+def twin_D(model: int, params, theta) -> np.ndarray:
+    p = pad_params(params)
+    th = np.atleast_1d(np.asarray(theta, dtype=np.float64))
+    out = np.empty((th.size, 3))
+    tmp = np.empty(3)
+    for k, t in enumerate(th.ravel()):
+        twin().fxt_D(model, _dp(p), float(t), _dp(tmp))
+        out[k] = tmp
+    return out.reshape(th.shape + (3,))
+
+
+def twin_solve_batch(model, params, b, i, itol: float = 1e-3, max_steps: int = 100, k_max: int = 0,
+                     nthreads: int = 0, max_ode_steps: int = 4096, rtol: float = 1e-3, atol: float = 1e-6,
+                     max_expansions: int = 64, radial_k: int = 0, ob: float = 0.0):
+    """Same outputs as the GPU entry point: summary[n,8], counters[n,8], knots[n,k_max,4]."""
+    model = np.ascontiguousarray(model, dtype=np.int32)
+    n = model.size
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(n, NPARAM)
+    b = np.ascontiguousarray(np.broadcast_to(np.asarray(b, dtype=np.float64), (n,)))
+    i = np.ascontiguousarray(np.broadcast_to(np.asarray(i, dtype=np.float64), (n,)))
+    summary = np.empty((n, NSUM))
+    counters = np.zeros((n, NCNT), dtype=np.int32)
+    knots = np.zeros((n, k_max, 4)) if k_max > 0 else None
+    twin().fxt_solve_batch(n, _ip(model), _dp(params), _dp(b), _dp(i), float(itol), int(max_steps),
+                           int(max_ode_steps), float(rtol), float(atol), int(max_expansions), int(radial_k),
+                           float(ob), _dp(summary), _ip(counters), k_max,
+                           _dp(knots) if knots is not None else None, int(nthreads))
+    return {"summary": summary, "counters": counters, "knots": knots}
 
 
 _lib = None
