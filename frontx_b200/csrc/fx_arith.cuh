@@ -60,7 +60,7 @@ struct Tol {
   double rtol, atol;
 };
 
-FX_HD double rms2(double a, double b) { return sqrt(fma(a, a, b * b)) * 0.70710678118654752440; }
+FX_HD double rms2(double a, double b) { return sqrt(fma(a, a, b * b)) * KC(K_RSQRT2); }
 
 // right-hand side of src/frontx/_boltzmann.py:27-33: [p, -((o/2 + D' p)/D) p]  (+ k/o radial term)
 struct Rhs {
@@ -86,7 +86,7 @@ FX_HD Chord chord_matrix(double D, double D1, double D2, const Rhs& r, double te
   double J10 = -ye1 * fma(D2 * ye1, D, -r.num * D1) * r.iD * r.iD;
   double J11 = -fma(2.0 * D1, ye1, 0.5 * te) * r.iD;
   if (radial_k) J11 -= (double)radial_k / te;
-  double g = GAMMA * h;
+  double g = KC(K_GAMMA) * h;
   double a11 = fma(g, J11, -1.0);
   double a10 = g * J10;
   double idet = 1.0 / fma(-g, a10, -a11);  // det of [[-1, g],[a10, a11]]
@@ -116,10 +116,10 @@ FX_HD void chord_decide(int iter, double size, double prev, bool& done, bool& ok
   if (iter >= 2) {
     double rate = size / prev;
     double factor = size * rate / (1.0 - rate);
-    bool small = size < 1e-13;
+    bool small = size < KC(K_1EM13);
     bool finite_rate = (rate - rate) == 0.0;
     bool diverged = !finite_rate || (rate > 2.0);
-    bool converged = (factor > 0.0) && (factor < 1e-2);
+    bool converged = (factor > 0.0) && (factor < KC(K_1EM2));
     done = small || diverged || converged;
     ok = small || (converged && !diverged);
     if (!done && iter >= 10) done = true;
@@ -131,8 +131,8 @@ FX_HD void init_h0(double y00, double y01, double F0, double F1, Tol tol, double
   double sc0 = fma(fabs(y00), tol.rtol, tol.atol), sc1 = fma(fabs(y01), tol.rtol, tol.atol);
   double d0 = rms2(y00 / sc0, y01 / sc1);
   d1 = rms2(F0 / sc0, F1 / sc1);
-  bool cond = (d0 < 1e-5) || (d1 < 1e-5);
-  h0 = cond ? 1e-6 : 0.01 * (d0 / d1);
+  bool cond = (d0 < KC(K_1EM5)) || (d1 < KC(K_1EM5));
+  h0 = cond ? KC(K_1EM6) : KC(K_0P01) * (d0 / d1);
 }
 // second half: dt0 from f(t0 + h0, y0 + h0 f0); error order 5
 FX_HD double init_dt(double y00, double y01, double f00, double f01, double F0, double F1, double h0,
@@ -140,7 +140,7 @@ FX_HD double init_dt(double y00, double y01, double f00, double f01, double F0, 
   double sc0 = fma(fabs(y00), tol.rtol, tol.atol), sc1 = fma(fabs(y01), tol.rtol, tol.atol);
   double d2 = rms2((F0 - f00) / sc0, (F1 - f01) / sc1) / h0;
   double max_d = fmax(d1, d2);
-  double h1 = (max_d <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : fx_exp(0.2 * fx_log(0.01 / max_d));
+  double h1 = (max_d <= KC(K_1EM15)) ? fmax(KC(K_1EM6), h0 * KC(K_1EM3)) : fx_exp(KC(K_0P2) * fx_log(KC(K_0P01) / max_d));
   return fmin(100.0 * h0, h1);
 }
 
@@ -168,7 +168,7 @@ FX_HD void stage_prepare(const Tableau& tab, int stage, FS fs, double y00, doubl
   te = fma(tab.c[stage], h, t0);
 }
 
-FX_HD double stage_point(double yp, double h, double f) { return fma(GAMMA, h * f, yp); }
+FX_HD double stage_point(double yp, double h, double f) { return fma(KC(K_GAMMA), h * f, yp); }
 
 // end of a step attempt: stiffly accurate y1, embedded error, I-controller
 struct StepEnd {
@@ -203,8 +203,8 @@ FX_HD StepEnd step_finish(const Tableau& tab, bool ok, FS fs, double y00, double
   double err = rms2(e0 / sc0, e1 / sc1);
   s.keep = err < 1.0;
   double inv = (err == 0.0) ? fx_inf() : 1.0 / err;
-  double factor = 0.9 * fx_exp(0.2 * fx_log(inv));
-  double fmin_ = s.keep ? 1.0 : 0.2;
+  double factor = KC(K_0P9) * fx_exp(KC(K_0P2) * fx_log(inv));
+  double fmin_ = s.keep ? 1.0 : KC(K_0P2);
   if (!(factor >= fmin_)) factor = fmin_;
   if (factor > 10.0) factor = 10.0;
   s.dt_next = h * factor;
