@@ -240,9 +240,10 @@ __global__ void eval_kernel(long long n, const int* __restrict__ counters,
 template <int MODEL>
 __device__ void diffusivity_one(const double* p, double th, double* out) {
   double d[fx::NDERIVED];
-  fx::derive_params<MODEL>(p, d);
+  fx::derive_params<MODEL>(p, d, fx::g_math_tab_dev);
   double D, D1, D2;
-  fx::eval_D<MODEL>(d, th, true, D, D1, D2);
+  double iD;
+  fx::eval_D<MODEL>(d, th, true, D, D1, D2, iD, fx::g_math_tab_dev);
   out[0] = D;
   out[1] = D1;
   out[2] = D2;

@@ -60,15 +60,19 @@ struct Tol {
   double rtol, atol;
 };
 
-FX_HD double rms2(double a, double b) { return sqrt(fma(a, a, b * b)) * KC(K_RSQRT2); }
+// root mean square of (a, b), squared: the controller's and the chord iteration's norm is
+// sqrt(mean(x^2)) (diffrax rms_norm); every test made on it is made on its square here,
+// which needs no square root
+FX_HD double ms2(double a, double b) { return 0.5 * fma(a, a, b * b); }
 
-// right-hand side of src/frontx/_boltzmann.py:27-33: [p, -((o/2 + D' p)/D) p]  (+ k/o radial term)
+// right-hand side of src/frontx/_boltzmann.py:27-33: [p, -((o/2 + D' p)/D) p]  (+ k/o radial term);
+// iD = 1/D comes from the model evaluation, which shares one reciprocal among its quotients
 struct Rhs {
   double F0, F1, iD, num;
 };
-FX_HD Rhs rhs_eval(double D, double D1, double te, double ye1, int radial_k) {
+FX_HD Rhs rhs_eval(double D1, double iD, double te, double ye1, int radial_k) {
   Rhs r;
-  r.iD = 1.0 / D;
+  r.iD = iD;
   r.num = fma(D1, ye1, 0.5 * te);  // o/2 + D' p
   double br = r.num * r.iD;
   if (radial_k) br += (double)radial_k / te;
@@ -89,7 +93,7 @@ FX_HD Chord chord_matrix(double D, double D1, double D2, const Rhs& r, double te
   double g = KC(K_GAMMA) * h;
   double a11 = fma(g, J11, -1.0);
   double a10 = g * J10;
-  double idet = 1.0 / fma(-g, a10, -a11);  // det of [[-1, g],[a10, a11]]
+  double idet = fx_rcp(fma(-g, a10, -a11));  // det of [[-1, g],[a10, a11]]
   Chord M;
   M.m00 = a11 * idet;
   M.m01 = -g * idet;
@@ -98,7 +102,8 @@ FX_HD Chord chord_matrix(double D, double D1, double D2, const Rhs& r, double te
   return M;
 }
 
-// one chord iteration on the stage derivative f: f -= M (F - f); returns the scaled step size
+// one chord iteration on the stage derivative f: f -= M (F - f); returns the SQUARE of the
+// scaled step size ||diff / (atol + rtol |f|)||_rms, from one shared reciprocal
 FX_HD double chord_update(const Chord& M, double F0, double F1, double& f0, double& f1, Tol tol) {
   double r0 = F0 - f0, r1 = F1 - f1;
   double dd0 = fma(M.m00, r0, M.m01 * r1);
@@ -106,20 +111,26 @@ FX_HD double chord_update(const Chord& M, double F0, double F1, double& f0, doub
   f0 -= dd0;
   f1 -= dd1;
   double s0 = fma(tol.rtol, fabs(f0), tol.atol), s1 = fma(tol.rtol, fabs(f1), tol.atol);
-  return rms2(dd0 / s0, dd1 / s1);
+  double ir = fx_rcp(s0 * s1);
+  return ms2(dd0 * s1 * ir, dd1 * s0 * ir);
 }
 
-// chord termination after `iter` iterations (optimistix Chord.terminate, max 10 steps)
-FX_HD void chord_decide(int iter, double size, double prev, bool& done, bool& ok) {
+// chord termination after `iter` iterations (optimistix Chord.terminate, max 10 steps), on
+// the squares S = size^2, P = prev^2 of the last two step sizes.  With rate = size/prev and
+// factor = size*rate/(1-rate) = size^2/(prev-size):
+//   small     = size < 1e-13                      <=>  S < 1e-26
+//   diverged  = !isfinite(rate) or rate > 2       <=>  !(S <= 4 P) or !(P > 0) or !(S < inf)
+//   converged = 0 < factor < kappa = 1e-2         <=>  L > 0 and L^2 > 4 kappa^2 S^3,
+//               L = kappa^2 (P - S) - S^2         (squaring kappa*prev > S + kappa*size twice)
+// so the iteration needs neither a division nor a square root.
+FX_HD void chord_decide(int iter, double S, double P, bool& done, bool& ok) {
   done = false;
   ok = false;
   if (iter >= 2) {
-    double rate = size / prev;
-    double factor = size * rate / (1.0 - rate);
-    bool small = size < KC(K_1EM13);
-    bool finite_rate = (rate - rate) == 0.0;
-    bool diverged = !finite_rate || (rate > 2.0);
-    bool converged = (factor > 0.0) && (factor < KC(K_1EM2));
+    bool small = S < KC(K_1EM26);
+    bool diverged = !(S <= 4.0 * P) || !(P > 0.0) || !(S < fx_inf());
+    double L = fma(KC(K_1EM4), P - S, -S * S);
+    bool converged = (L > 0.0) && (L * L > KC(K_4EM4) * S * S * S);
     done = small || diverged || converged;
     ok = small || (converged && !diverged);
     if (!done && iter >= 10) done = true;
@@ -129,18 +140,20 @@ FX_HD void chord_decide(int iter, double size, double prev, bool& done, bool& ok
 // Hairer initial step, first half: h0 and d1 from f(t0, y0)
 FX_HD void init_h0(double y00, double y01, double F0, double F1, Tol tol, double& h0, double& d1) {
   double sc0 = fma(fabs(y00), tol.rtol, tol.atol), sc1 = fma(fabs(y01), tol.rtol, tol.atol);
-  double d0 = rms2(y00 / sc0, y01 / sc1);
-  d1 = rms2(F0 / sc0, F1 / sc1);
+  double i0 = fx_rcp(sc0), i1 = fx_rcp(sc1);
+  double d0 = sqrt(ms2(y00 * i0, y01 * i1));
+  d1 = sqrt(ms2(F0 * i0, F1 * i1));
   bool cond = (d0 < KC(K_1EM5)) || (d1 < KC(K_1EM5));
-  h0 = cond ? KC(K_1EM6) : KC(K_0P01) * (d0 / d1);
+  h0 = cond ? KC(K_1EM6) : KC(K_0P01) * (d0 * fx_rcp(d1));
 }
 // second half: dt0 from f(t0 + h0, y0 + h0 f0); error order 5
 FX_HD double init_dt(double y00, double y01, double f00, double f01, double F0, double F1, double h0,
-                     double d1, Tol tol) {
+                     double d1, Tol tol, const MathTab& T) {
   double sc0 = fma(fabs(y00), tol.rtol, tol.atol), sc1 = fma(fabs(y01), tol.rtol, tol.atol);
-  double d2 = rms2((F0 - f00) / sc0, (F1 - f01) / sc1) / h0;
+  double d2 = sqrt(ms2((F0 - f00) * fx_rcp(sc0), (F1 - f01) * fx_rcp(sc1))) * fx_rcp(h0);
   double max_d = fmax(d1, d2);
-  double h1 = (max_d <= KC(K_1EM15)) ? fmax(KC(K_1EM6), h0 * KC(K_1EM3)) : fx_exp(KC(K_0P2) * fx_log(KC(K_0P01) / max_d));
+  double h1 = (max_d <= KC(K_1EM15)) ? fmax(KC(K_1EM6), h0 * KC(K_1EM3))
+                                     : fx_exp(KC(K_0P2) * fx_log(KC(K_0P01) * fx_rcp(max_d), T), T);
   return fmin(100.0 * h0, h1);
 }
 
@@ -171,42 +184,47 @@ FX_HD void stage_prepare(const Tableau& tab, int stage, FS fs, double y00, doubl
 FX_HD double stage_point(double yp, double h, double f) { return fma(KC(K_GAMMA), h * f, yp); }
 
 // end of a step attempt: stiffly accurate y1, embedded error, I-controller
+// (PIDController(rtol, atol) with pcoeff = dcoeff = 0: factor = 0.9 err^(-1/5) clipped to
+// [0.2 or 1, 10]; accept iff err < 1).  Works on E2 = err^2: err < 1 <=> E2 < 1 and
+// err^(-1/5) = E2^(-1/10), so no square root is taken.  A failed implicit solve or a NaN error
+// estimate is err = inf: rejected, dt <- 0.2 dt, with no arithmetic on infinities.
 struct StepEnd {
   double y10, y11, dt_next;
   bool keep;
 };
 template <class FS>
 FX_HD StepEnd step_finish(const Tableau& tab, bool ok, FS fs, double y00, double y01, double yp0, double yp1,
-                          double f0, double f1, double h, Tol tol) {
+                          double f0, double f1, double h, Tol tol, const MathTab& T) {
   StepEnd s;
   s.y10 = y00;
   s.y11 = y01;
-  double e0 = fx_inf(), e1 = fx_inf();  // failed implicit solve => err = inf => reject, shrink
-  if (ok) {
-    s.y10 = stage_point(yp0, h, f0);
-    s.y11 = stage_point(yp1, h, f1);
-    double a0 = 0.0, a1 = 0.0;
+  s.keep = false;
+  s.dt_next = h * KC(K_0P2);
+  if (!ok) return s;
+  s.y10 = stage_point(yp0, h, f0);
+  s.y11 = stage_point(yp1, h, f1);
+  double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-    for (int j = 0; j < 7; j++) {
-      a0 = fma(tab.berr[j], fs(j, 0), a0);
-      a1 = fma(tab.berr[j], fs(j, 1), a1);
-    }
-    e0 = h * a0;
-    e1 = h * a1;
-    if (e0 != e0) e0 = fx_inf();
-    if (e1 != e1) e1 = fx_inf();
+  for (int j = 0; j < 7; j++) {
+    a0 = fma(tab.berr[j], fs(j, 0), a0);
+    a1 = fma(tab.berr[j], fs(j, 1), a1);
   }
+  double e0 = h * a0, e1 = h * a1;
   bool nan1 = (s.y10 != s.y10) || (s.y11 != s.y11);
   double q0 = nan1 ? y00 : s.y10, q1 = nan1 ? y01 : s.y11;
   double sc0 = fma(fmax(fabs(y00), fabs(q0)), tol.rtol, tol.atol);
   double sc1 = fma(fmax(fabs(y01), fabs(q1)), tol.rtol, tol.atol);
-  double err = rms2(e0 / sc0, e1 / sc1);
-  s.keep = err < 1.0;
-  double inv = (err == 0.0) ? fx_inf() : 1.0 / err;
-  double factor = KC(K_0P9) * fx_exp(KC(K_0P2) * fx_log(inv));
-  double fmin_ = s.keep ? 1.0 : KC(K_0P2);
-  if (!(factor >= fmin_)) factor = fmin_;
-  if (factor > 10.0) factor = 10.0;
+  double ir = fx_rcp(sc0 * sc1);
+  double E2 = ms2(e0 * sc1 * ir, e1 * sc0 * ir);
+  if (!(E2 < fx_inf())) return s;  // inf or NaN error estimate: reject and shrink
+  s.keep = E2 < 1.0;
+  double factor = 10.0;
+  if (E2 > 0.0) {
+    factor = KC(K_0P9) * fx_exp(-KC(K_0P1) * fx_log(E2, T), T);
+    double fmin_ = s.keep ? 1.0 : KC(K_0P2);
+    if (!(factor >= fmin_)) factor = fmin_;
+    if (factor > 10.0) factor = 10.0;
+  }
   s.dt_next = h * factor;
   return s;
 }

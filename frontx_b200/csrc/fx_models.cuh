@@ -5,7 +5,7 @@
 // (src/frontx/_boltzmann.py:29, src/frontx/models.py:95-100); here they are
 // hand-derived logarithmic-derivative forms that share one log per base
 // (log Se, log(1-Se)) and use exp() for every power, so that a van Genuchten
-// evaluation costs 2 log + 3 exp instead of 5+ pow calls.
+// evaluation costs 2 log + 3 exp + ONE reciprocal instead of 5+ pow calls and 7 divisions.
 //
 //   Se = (theta - theta_r)/(theta_s - theta_r)          models.py:17-24
 //   LETd            D = Dwt Se^L/(Se^L + E (1-Se)^T)    models.py:62-66
@@ -22,15 +22,16 @@
 
 namespace fx {
 
-constexpr int NDERIVED = 10;
+constexpr int NDERIVED = 12;
 
 // Per-problem derived constants, computed once when a thread picks a problem up.
 template <int MODEL>
-FX_HD void derive_params(const double* p, double (&d)[NDERIVED]) {
+FX_HD void derive_params(const double* p, double (&d)[NDERIVED], const MathTab& T) {
 #pragma unroll
   for (int k = 0; k < NDERIVED; k++) d[k] = 0.0;
   if constexpr (MODEL == FX_CONSTANT) {
     d[0] = p[0];
+    d[1] = fx_rcp(p[0]);
   } else if constexpr (MODEL == FX_POWER_LAW) {
     d[0] = p[0];  // a
     d[1] = p[1];  // k
@@ -51,6 +52,7 @@ FX_HD void derive_params(const double* p, double (&d)[NDERIVED]) {
     d[2] = tr;
     d[3] = dT;
     d[4] = 1.0 / dT;
+    d[5] = 1.0 / d[1];
   } else if constexpr (MODEL == FX_VAN_GENUCHTEN) {
     double m = p[1], l = p[2], Ks = p[3], alpha = p[4], tr = p[5], ts = p[6];
     double dT = ts - tr;
@@ -61,79 +63,102 @@ FX_HD void derive_params(const double* p, double (&d)[NDERIVED]) {
     d[4] = tr;
     d[5] = dT;
     d[6] = 1.0 / dT;
+    d[7] = 1.0 / d[3];
   } else if constexpr (MODEL == FX_LETD) {
     double tr = p[4], ts = p[5];
     double dT = ts - tr;
-    d[0] = p[0];          // L
-    d[1] = fx_log(p[1]);  // ln E
-    d[2] = p[2];          // T
-    d[3] = p[3];          // Dwt
+    d[0] = p[0];             // L
+    d[1] = fx_log(p[1], T);  // ln E
+    d[2] = p[2];             // T
+    d[3] = p[3];             // Dwt
     d[4] = tr;
     d[5] = dT;
     d[6] = 1.0 / dT;
+    d[7] = 1.0 / p[3];
   } else if constexpr (MODEL == FX_LETXS) {
     double Ks = p[6], alpha = p[7], tr = p[8], ts = p[9];
     double dT = ts - tr;
-    d[0] = p[0];           // Lw
-    d[1] = fx_log(p[1]);   // ln Ew
-    d[2] = p[2];           // Tw
-    d[3] = p[3];           // Ls
-    d[4] = fx_log(p[4]);   // ln Es
-    d[5] = p[5];           // Ts
+    d[0] = p[0];              // Lw
+    d[1] = fx_log(p[1], T);   // ln Ew
+    d[2] = p[2];              // Tw
+    d[3] = p[3];              // Ls
+    d[4] = fx_log(p[4], T);   // ln Es
+    d[5] = p[5];              // Ts
     d[6] = Ks / (alpha * dT);  // Cc
     d[7] = tr;
     d[8] = dT;
     d[9] = 1.0 / dT;
+    d[10] = 1.0 / d[6];
   }
 }
 
-// D, D' and (when want2) D'' at theta.  NaN outside the model's domain, like
-// pow() of a negative base in the reference.
+// D, D', (when want2) D'' and 1/D at theta.  NaN outside the model's domain, like pow() of a
+// negative base in the reference.  All quotients of one evaluation are formed from ONE
+// reciprocal (of the product of the denominators, unwound by multiplications): an fp64
+// reciprocal costs about ten multiply-adds on sm_100a.
 template <int MODEL>
 FX_HD void eval_D(const double (&d)[NDERIVED], double theta, bool want2, double& D, double& D1,
-                  double& D2) {
+                  double& D2, double& iD, const MathTab& T) {
   D2 = 0.0;
   if constexpr (MODEL == FX_CONSTANT) {
     D = d[0];
     D1 = 0.0;
+    iD = d[1];
   } else if constexpr (MODEL == FX_POWER_LAW) {
     double a = d[0], k = d[1], eps = d[2];
-    double mag = fx_exp(k * fx_log(fabs(theta)));
+    double mag = fx_exp(k * fx_log(fabs(theta), T), T);
     double sgn = (theta < 0.0) ? d[3] : 1.0;  // NaN for non-integer k
     double pw = a * sgn * mag;
-    double it = 1.0 / theta;
     D = pw + eps;
+    double ip = fx_rcp(theta * D);
+    double it = D * ip;
+    iD = theta * ip;
     D1 = k * pw * it;
     if (want2) D2 = (k - 1.0) * D1 * it;
   } else if constexpr (MODEL == FX_LOG) {
-    double it = 1.0 / theta;
-    D = fma(d[1], fx_log(theta), d[0]);
+    D = fma(d[1], fx_log(theta, T), d[0]);
+    double ip = fx_rcp(theta * D);
+    double it = D * ip;
+    iD = theta * ip;
     D1 = d[1] * it;
     if (want2) D2 = -D1 * it;
   } else if constexpr (MODEL == FX_BROOKS_COREY) {
-    double e = d[0], Cc = d[1], tr = d[2], dT = d[3], idT = d[4];
-    double Se = (theta - tr) / dT;
-    double L = fx_log(Se);
-    double iSe = idT / Se;  // (1/Se) * dSe/dtheta
-    D = Cc * fx_exp(e * L);
+    double e = d[0], Cc = d[1], tr = d[2], dT = d[3], idT = d[4], iCc = d[5];
+    double Se = div_by(theta - tr, dT, idT);
+    double L = fx_log(Se, T);
+    double E = fx_exp(e * L, T);   // Se^e
+    double ip = fx_rcp(Se * E);
+    double iSe = idT * (E * ip);   // (1/Se) * dSe/dtheta
+    D = Cc * E;
+    iD = iCc * (Se * ip);
     D1 = D * e * iSe;
     if (want2) D2 = D1 * (e - 1.0) * iSe;
   } else if constexpr (MODEL == FX_VAN_GENUCHTEN) {
-    double im = d[0], m = d[1], a = d[2], Cc = d[3], tr = d[4], dT = d[5], idT = d[6];
-    double Se = (theta - tr) / dT;
-    double L = fx_log(Se);
+    double im = d[0], m = d[1], a = d[2], Cc = d[3], tr = d[4], dT = d[5], idT = d[6], iCc = d[7];
+    double Se = div_by(theta - tr, dT, idT);
+    double L = fx_log(Se, T);
     // w = 1 - Se^(1/m) has condition number ~1e7 at b = theta_s - 1e-7 (the reference's own
     // test point); form it without cancellation so that implementations agree to ~1e-15
-    double w = -fx_expm1(im * L);
-    double u = 1.0 - w;               // Se^(1/m)
-    double v = fx_exp(m * fx_log(w)); // (1 - Se^(1/m))^m
+    double w = -fx_expm1(im * L, T);
+    double u = 1.0 - w;                     // Se^(1/m)
+    double v = fx_exp(m * fx_log(w, T), T); // (1 - Se^(1/m))^m
     double omv = 1.0 - v;
-    double iSe = 1.0 / Se, iw = 1.0 / w, iomv = 1.0 / omv;
-    double g = fx_exp(a * L) * omv * omv / v;   // Se^a (1-v)^2 / v
-    double q = -u * iw * iSe;                   // v'/v
+    double E = fx_exp(a * L, T);            // Se^a
+    // reciprocals of Se, w, 1-v, v, E from one
+    double p2 = Se * w, p3 = p2 * omv, p4 = p3 * v;
+    double R = fx_rcp(p4 * E);
+    double iE = R * p4;
+    R *= E;
+    double iv = R * p3;
+    R *= v;
+    double iomv = R * p2;
+    R *= omv;
+    double iw = R * Se, iSe = R * w;
+    double q = -u * iw * iSe;               // v'/v
     double r = (1.0 + v) * iomv;
-    double lg1 = fma(a, iSe, -q * r);           // (ln g)'
-    D = Cc * g;
+    double lg1 = fma(a, iSe, -q * r);       // (ln g)',  g = Se^a (1-v)^2 / v
+    D = Cc * (E * omv * omv * iv);
+    iD = iCc * (iE * iomv * iomv * v);
     D1 = D * lg1 * idT;
     if (want2) {
       double q1 = q * iSe * fma(im, iw, -1.0);            // q'
@@ -142,40 +167,55 @@ FX_HD void eval_D(const double (&d)[NDERIVED], double theta, bool want2, double&
       D2 = D * fma(lg1, lg1, lg2) * idT * idT;
     }
   } else if constexpr (MODEL == FX_LETD) {
-    double Lx = d[0], lnE = d[1], T = d[2], Dwt = d[3], tr = d[4], dT = d[5], idT = d[6];
-    double Se = (theta - tr) / dT;
+    double Lx = d[0], lnE = d[1], Tx = d[2], Dwt = d[3], tr = d[4], dT = d[5], idT = d[6], iDwt = d[7];
+    double Se = div_by(theta - tr, dT, idT);
     double oms = 1.0 - Se;
-    double L1 = fx_log(Se), L2 = fx_log(oms);
-    double R = fx_exp(fma(T, L2, fma(-Lx, L1, lnE)));  // E (1-Se)^T / Se^L
-    double iSe = 1.0 / Se, ioms = 1.0 / oms;
-    double rho = fma(-T, ioms, -Lx * iSe);             // R'/R
-    double qq = 1.0 / (1.0 + R);
+    double L1 = fx_log(Se, T), L2 = fx_log(oms, T);
+    double R = fx_exp(fma(Tx, L2, fma(-Lx, L1, lnE)), T);  // E (1-Se)^T / Se^L
+    double opR = 1.0 + R;
+    double p2 = Se * oms;
+    double ip = fx_rcp(p2 * opR);
+    double qq = ip * p2;                                   // 1/(1+R)
+    double ir = ip * opR;
+    double iSe = ir * oms, ioms = ir * Se;
+    double rho = fma(-Tx, ioms, -Lx * iSe);                // R'/R
     double R1 = R * rho;
     D = Dwt * qq;
+    iD = iDwt * opR;
     D1 = -Dwt * R1 * qq * qq * idT;
     if (want2) {
-      double rho1 = fma(-T * ioms, ioms, Lx * iSe * iSe);
+      double rho1 = fma(-Tx * ioms, ioms, Lx * iSe * iSe);
       double R2 = R * fma(rho, rho, rho1);
       D2 = -Dwt * fma(-2.0 * R1 * R1, qq, R2) * qq * qq * idT * idT;
     }
   } else if constexpr (MODEL == FX_LETXS) {
     double Lw = d[0], lnEw = d[1], Tw = d[2], Ls = d[3], lnEs = d[4], Ts = d[5], Cc = d[6];
-    double tr = d[7], dT = d[8], idT = d[9];
-    double Se = (theta - tr) / dT;
+    double tr = d[7], dT = d[8], idT = d[9], iCc = d[10];
+    double Se = div_by(theta - tr, dT, idT);
     double oms = 1.0 - Se;
-    double L1 = fx_log(Se), L2 = fx_log(oms);
-    double R = fx_exp(fma(Tw, L2, fma(-Lw, L1, lnEw)));  // Ew (1-Se)^Tw / Se^Lw  -> kr = 1/(1+R)
-    double S = fx_exp(fma(Ts, L1, fma(-Ls, L2, lnEs)));  // Q/P = Es Se^Ts / (1-Se)^Ls
-    double iSe = 1.0 / Se, ioms = 1.0 / oms;
-    double kr = 1.0 / (1.0 + R), qs = 1.0 / (1.0 + S);
+    double L1 = fx_log(Se, T), L2 = fx_log(oms, T);
+    double R = fx_exp(fma(Tw, L2, fma(-Lw, L1, lnEw)), T);  // Ew (1-Se)^Tw / Se^Lw  -> kr = 1/(1+R)
+    double S = fx_exp(fma(Ts, L1, fma(-Ls, L2, lnEs)), T);  // Q/P = Es Se^Ts / (1-Se)^Ls
+    double opR = 1.0 + R, opS = 1.0 + S;
+    // reciprocals of Se, 1-Se, 1+R, 1+S from one
+    double p2 = Se * oms, p3 = p2 * opR;
+    double Rr = fx_rcp(p3 * opS);
+    double qs = Rr * p3;
+    Rr *= opS;
+    double kr = Rr * p2;
+    Rr *= opR;
+    double ioms = Rr * Se, iSe = Rr * oms;
     double A = R * kr, B = S * qs;
     double sig = fma(Ls, ioms, Ts * iSe);
     double sig1 = fma(Ls * ioms, ioms, -Ts * iSe * iSe);
     double rho = fma(-Tw, ioms, -Lw * iSe);
-    double isig = 1.0 / sig;
+    D = Cc * kr * B * qs * sig;
+    double ip = fx_rcp(sig * D);
+    double isig = D * ip;
+    iD = sig * ip;
+    (void)iCc;
     double omb2 = fma(-2.0, B, 1.0);
     double G1 = fma(-rho, A, fma(sig, omb2, sig1 * isig));  // (ln D)' wrt Se
-    D = Cc * kr * B * qs * sig;
     D1 = D * G1 * idT;
     if (want2) {
       double rho1 = fma(-Tw * ioms, ioms, Lw * iSe * iSe);

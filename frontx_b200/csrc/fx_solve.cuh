@@ -67,6 +67,7 @@ enum Mode : int { M_FETCH = 0, M_DB = 1, M_INIT0 = 2, M_INIT1 = 3, M_CHORD = 4, 
 template <int MODEL, bool RADIAL>
 __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveArgs A) {
   __shared__ Tableau tab;
+  __shared__ MathTab mt;                     // log / exp lookup tables (lanes index them divergently)
   __shared__ double fsm[7][2][SOLVE_BLOCK];  // stage derivatives, one column per thread
 
   const int tid = threadIdx.x;
@@ -74,6 +75,9 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
     const double* src = reinterpret_cast<const double*>(&c_tab);
     double* dst = reinterpret_cast<double*>(&tab);
     for (int k = tid; k < (int)(sizeof(Tableau) / sizeof(double)); k += SOLVE_BLOCK) dst[k] = src[k];
+    src = reinterpret_cast<const double*>(&g_math_tab_dev);
+    dst = reinterpret_cast<double*>(&mt);
+    for (int k = tid; k < (int)(sizeof(MathTab) / sizeof(double)); k += SOLVE_BLOCK) dst[k] = src[k];
   }
   __syncthreads();
 
@@ -108,10 +112,11 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
   double yp0 = 0, yp1 = 0;                 // y_partial of the current stage
   double f0 = 0, f1 = 0;                   // chord iterate (stage derivative)
   Chord M = {0, 0, 0, 0};                  // inverse of gamma*h*J - I
-  double dsz = 0;                          // previous chord step size
+  double dsz = 0;                          // square of the previous chord step size
   double te = 0, ye0 = 0, ye1 = 0;         // where the next RHS is evaluated
   int stage = 1, iter = 0, att_shot = 0;
   int n_shots = 0, n_att = 0, n_rej = 0, n_rhs = 0, n_jac = 0, n_knots = 0;
+  int rhs_mark = 0, rej_mark = 0;          // counters at the start of the current shot
   double* knot_row = nullptr;
 
   for (;;) {
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
         if (w < n_work) {
           prob = perm ? (long long)perm[w] : w;
           const double* p = A.params + prob * FX_NPARAM;
-          derive_params<MODEL>(p, dpar);
+          derive_params<MODEL>(p, dpar, mt);
           bnd_b = A.b[prob];
           bnd_i = A.i[prob];
           direction = (bnd_i > bnd_b) ? 1.0 : ((bnd_i < bnd_b) ? -1.0 : 0.0);
@@ -146,9 +151,9 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
 
     // ---- the one expensive thing per trip: a right-hand-side evaluation ---
     const bool wantJ = (mode == M_CHORD) && (stage == 1) && (iter == 0);
-    double D, D1, D2;
-    eval_D<MODEL>(dpar, ye0, wantJ, D, D1, D2);
-    const Rhs R = rhs_eval(D, D1, te, ye1, radial_k);
+    double D, D1, D2, iD;
+    eval_D<MODEL>(dpar, ye0, wantJ, D, D1, D2, iD, mt);
+    const Rhs R = rhs_eval(D1, iD, te, ye1, radial_k);
 
     bool att_end = false, att_ok = false, shot_end = false, occurred = false;
     bool start_shot = false, prep = false;
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       mode = M_INIT1;
     } else if (mode == M_INIT1) {
       n_rhs++;
-      double dt = init_dt(y00, y01, fs(0, 0), fs(0, 1), R.F0, R.F1, h, dsz, tol);
+      double dt = init_dt(y00, y01, fs(0, 0), fs(0, 1), R.F0, R.F1, h, dsz, tol, mt);
       t1 = t0 + dt;
       h = t1 - t0;
       stage = 1;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
     if (att_end) {
       n_att++;
       att_shot++;
-      StepEnd s = step_finish(tab, att_ok, fs, y00, y01, yp0, yp1, f0, f1, h, tol);
+      StepEnd s = step_finish(tab, att_ok, fs, y00, y01, yp0, yp1, f0, f1, h, tol, mt);
       if (s.keep) {
         t0 = t1;
         y00 = s.y10;
@@ -246,7 +251,20 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       double res = occurred ? (y00 - bnd_i) : direction * fx_inf();  // _forward.py:97-101
       n_shots++;
       double d_shot = bis.d_cur;
+      const int rhs_shot = n_rhs - rhs_mark, rej_shot = n_rej - rej_mark;
       int result = bis.next(res, A.itol, A.max_bisect, A.max_expansions);
+      // A shot is a pure function of d_dob.  Once the bracket has collapsed to two adjacent
+      // doubles without |res| < itol, the midpoint is one of its ends and every remaining
+      // bisection step repeats the shot just made: replay its residual and counters
+      // instead of integrating again (the knot row it wrote is the same too).
+      while (result < 0 && bis.d_cur == d_shot) {
+        n_shots++;
+        n_att += att_shot;
+        n_rej += rej_shot;
+        n_rhs += rhs_shot;
+        n_jac += att_shot;
+        result = bis.next(res, A.itol, A.max_bisect, A.max_expansions);
+      }
       if (result < 0) {
         start_shot = true;
       } else {
@@ -267,6 +285,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       y00 = bnd_b;
       y01 = bis.d_cur;
       att_shot = 0;
+      rhs_mark = n_rhs;
+      rej_mark = n_rej;
       te = t0;
       ye0 = y00;
       ye1 = y01;

@@ -35,6 +35,7 @@
 namespace {
 
 const fx::Tableau h_tab = FX_TABLEAU_INIT;
+const fx::MathTab& MT = fx::g_math_tab_host;
 
 struct Options {
   double itol, rtol, atol, ob;
@@ -58,11 +59,11 @@ Shot shoot(const double (&dpar)[fx::NDERIVED], double b, double i, double d_dob,
   double fsv[7][2];
   auto fs = [&](int j, int k) -> double { return fsv[j][k]; };
   double t0 = o.ob, y00 = b, y01 = d_dob;
-  double D, D1, D2;
+  double D, D1, D2, iD;
 
   // solver.init and the initial step size (two right-hand sides)
-  eval_D<MODEL>(dpar, y00, false, D, D1, D2);
-  Rhs R = rhs_eval(D, D1, t0, y01, o.radial_k);
+  eval_D<MODEL>(dpar, y00, false, D, D1, D2, iD, MT);
+  Rhs R = rhs_eval(D1, iD, t0, y01, o.radial_k);
   c.n_rhs++;
   fsv[0][0] = R.F0;
   fsv[0][1] = R.F1;
@@ -70,10 +71,10 @@ Shot shoot(const double (&dpar)[fx::NDERIVED], double b, double i, double d_dob,
   c.n_knots = 1;
   double h0, d1;
   init_h0(y00, y01, R.F0, R.F1, tol, h0, d1);
-  eval_D<MODEL>(dpar, fma(h0, R.F0, y00), false, D, D1, D2);
-  Rhs R1 = rhs_eval(D, D1, t0 + h0, fma(h0, R.F1, y01), o.radial_k);
+  eval_D<MODEL>(dpar, fma(h0, R.F0, y00), false, D, D1, D2, iD, MT);
+  Rhs R1 = rhs_eval(D1, iD, t0 + h0, fma(h0, R.F1, y01), o.radial_k);
   c.n_rhs++;
-  double dt = init_dt(y00, y01, fsv[0][0], fsv[0][1], R1.F0, R1.F1, h0, d1, tol);
+  double dt = init_dt(y00, y01, fsv[0][0], fsv[0][1], R1.F0, R1.F1, h0, d1, tol, MT);
   double t1 = t0 + dt;
 
   bool occurred = false;
@@ -88,8 +89,8 @@ Shot shoot(const double (&dpar)[fx::NDERIVED], double b, double i, double d_dob,
       for (int iter = 0;;) {
         double ye0 = stage_point(yp0, h, f0), ye1 = stage_point(yp1, h, f1);
         bool wantJ = (stage == 1) && (iter == 0);
-        eval_D<MODEL>(dpar, ye0, wantJ, D, D1, D2);
-        Rhs Rs = rhs_eval(D, D1, te, ye1, o.radial_k);
+        eval_D<MODEL>(dpar, ye0, wantJ, D, D1, D2, iD, MT);
+        Rhs Rs = rhs_eval(D1, iD, te, ye1, o.radial_k);
         c.n_rhs++;
         if (wantJ) {
           M = chord_matrix(D, D1, D2, Rs, te, ye1, h, o.radial_k);
@@ -112,7 +113,7 @@ Shot shoot(const double (&dpar)[fx::NDERIVED], double b, double i, double d_dob,
     }
     att++;
     c.n_att++;
-    StepEnd s = step_finish(h_tab, ok, fs, y00, y01, yp0, yp1, f0, f1, h, tol);
+    StepEnd s = step_finish(h_tab, ok, fs, y00, y01, yp0, yp1, f0, f1, h, tol, MT);
     if (s.keep) {
       t0 = t1;
       y00 = s.y10;
@@ -145,9 +146,9 @@ int solve_one(const double* p, double b, double i, const Options& o, double* sum
               int k_max, double* knots) {
   using namespace fx;
   double dpar[NDERIVED];
-  derive_params<MODEL>(p, dpar);
-  double D, D1, D2;
-  eval_D<MODEL>(dpar, b, false, D, D1, D2);
+  derive_params<MODEL>(p, dpar, MT);
+  double D, D1, D2, iD;
+  eval_D<MODEL>(dpar, b, false, D, D1, D2, iD, MT);
   const double D_b = D;
   Bisect bis;
   bis.start(D_b, b, i);
@@ -197,8 +198,9 @@ int solve_dispatch(int model, const double* p, double b, double i, const Options
 template <int MODEL>
 void D_one(const double* p, double theta, double* out) {
   double d[fx::NDERIVED];
-  fx::derive_params<MODEL>(p, d);
-  fx::eval_D<MODEL>(d, theta, true, out[0], out[1], out[2]);
+  fx::derive_params<MODEL>(p, d, MT);
+  double iD;
+  fx::eval_D<MODEL>(d, theta, true, out[0], out[1], out[2], iD, MT);
 }
 
 struct Batch {
@@ -244,9 +246,9 @@ void fxt_D(int model, const double* p, double theta, double* out) {
   }
 }
 
-double fxt_log(double x) { return fx::fx_log(x); }
-double fxt_exp(double x) { return fx::fx_exp(x); }
-double fxt_expm1(double x) { return fx::fx_expm1(x); }
+double fxt_log(double x) { return fx::fx_log(x, MT); }
+double fxt_exp(double x) { return fx::fx_exp(x, MT); }
+double fxt_expm1(double x) { return fx::fx_expm1(x, MT); }
 
 int fxt_solve_batch(int64_t n, const int32_t* model, const double* params, const double* b, const double* i,
                     double itol, int max_bisect, int max_ode_steps, double rtol, double atol,

@@ -37,7 +37,7 @@ class Options(C.Structure):
 def build(force: bool = False) -> Path:
     csrc = HERE.parent / "frontx_b200" / "csrc"
     srcs = [HERE / "fx_oracle.c", HERE / "fx_oracle_inverse.c", HERE / "fx_oracle.h", HERE / "fx_twin.cpp",
-            HERE / "Makefile", csrc / "fx_math.cuh", csrc / "fx_models.cuh", csrc / "fx_arith.cuh"]
+            HERE / "Makefile", csrc / "fx_math.cuh", csrc / "fx_tables.inc", csrc / "fx_models.cuh", csrc / "fx_arith.cuh"]
     libs = [LIB, HERE / "libfx_twin.so", HERE / "libfx_twin_fma.so"]
     stale = any(not p.exists() for p in libs) or any(
         s.stat().st_mtime > min(p.stat().st_mtime for p in libs) for s in srcs if s.exists())

@@ -1,6 +1,6 @@
 """Aggregate an ncu SASS source page by CUDA source line.
 
-usage: ncu_by_line.py <report.ncu-rep> <lib.so> <mangled-kernel-name-substring>
+usage: ncu_by_line.py <report.ncu-rep> <lib.so> <mangled-kernel-name-substring> [demangled-name substring selecting the launch, e.g. "<(int)3"]
 
 `ncu --page source --csv` gives per-SASS-instruction counters without the CUDA
 line; nvdisasm -g on the same binary gives the line of every instruction.  The
@@ -34,6 +34,11 @@ for l in sass[start + 1:]:
         seq.append((int(m.group(1), 16), cur, m.group(2)))
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.split("\n")))
+# one section per profiled launch, each headed by a "Kernel Name" row; keep the selected one
+heads = [k for k, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+pick = sys.argv[4] if len(sys.argv) > 4 else ""
+sel = [k for k in range(len(heads) - 1) if pick in rows[heads[k]][1]][0]
+rows = rows[heads[sel]:heads[sel + 1]]
 hdr = rows[1]
 ie, te, sm = hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed"), hdr.index("# Samples")
 prof = [(r[1], float(r[ie]), float(r[te]), float(r[sm] or 0)) for r in rows[2:] if len(r) > ie]
