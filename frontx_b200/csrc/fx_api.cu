@@ -130,7 +130,9 @@ int launch_by_id(int model, const fx::SolveArgs& a, bool radial, long long n_upp
   if (bps < 1) bps = 1;
   long long want = (n_upper + fx::SOLVE_BLOCK - 1) / fx::SOLVE_BLOCK;
   long long cap = (long long)sms * bps;  // persistent grid: every CTA resident
-  int grid = (int)(want < cap ? want : cap);
+  // whole CTAs per SM, the same number on every SM (the work queue hands lanes beyond n nothing)
+  long long even = (want + sms - 1) / sms * sms;
+  int grid = (int)(even < cap ? even : cap);
   if (grid < 1) grid = 1;
   switch (model) {
     case FX_CONSTANT: return launch_model<FX_CONSTANT>(a, radial, grid, s);
