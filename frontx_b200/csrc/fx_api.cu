@@ -50,8 +50,8 @@ int device_info(DeviceInfo* out) {
 }
 
 // ---- bucketing of a mixed batch by model -----------------------------------
-// scratch layout (unsigned long long): counts[8] | cursors[8] | queues[8]
-constexpr int SCR_COUNTS = 0, SCR_CURSORS = 8, SCR_QUEUES = 16, SCR_WORDS = 24;
+// scratch layout (unsigned long long): counts[8] | cursors[8] | speculation-slot allocator
+constexpr int SCR_COUNTS = 0, SCR_CURSORS = 8, SCR_WORDS = 16;
 
 __global__ void count_models_kernel(long long n, const int* __restrict__ model_id,
                                     unsigned long long* scratch) {
@@ -358,22 +358,42 @@ int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, con
   if ((rc = get_fork(&fk))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
 
-  // scratch: bucket counters + permutation, stream-ordered
+  // scratch, stream-ordered: bucket counters + permutation, the queue control blocks, the shot
+  // ring (one region per bucket: its problems + one spare entry per resident lane), 8 bytes of
+  // bisection state per problem, and the speculation slots
+  const long long max_lanes = (long long)di.sms * 2048;
+  const long long ring_pad = max_lanes + 64;
+  const size_t ring_words = (size_t)n + 8 * (size_t)ring_pad;
+  long long spec_slots = max_lanes / 3 + 8;
+  if (spec_slots > n) spec_slots = n;
+  if (k_max > 0) spec_slots = 0;  // dense output requested: the last shot must write its knots itself
   unsigned long long* scratch = nullptr;
   int* perm = nullptr;
-  FX_CUDA(cudaMallocAsync((void**)&scratch, SCR_WORDS * sizeof(unsigned long long), s));
+  fx::QueueCtl* ctl = nullptr;
+  unsigned long long* ring = nullptr;
+  int2* bstate = nullptr;
+  fx::SpecEntry* spec = nullptr;
+  FX_CUDA(cudaMallocAsync((void**)&scratch, (SCR_WORDS + 8) * sizeof(unsigned long long), s));
   FX_CUDA(cudaMallocAsync((void**)&perm, (size_t)n * sizeof(int), s));
-  FX_CUDA(cudaMemsetAsync(scratch, 0, SCR_WORDS * sizeof(unsigned long long), s));
+  FX_CUDA(cudaMallocAsync((void**)&ctl, 8 * sizeof(fx::QueueCtl), s));
+  FX_CUDA(cudaMallocAsync((void**)&ring, ring_words * sizeof(unsigned long long), s));
+  FX_CUDA(cudaMallocAsync((void**)&bstate, (size_t)n * sizeof(int2), s));
+  if (spec_slots > 0)
+    FX_CUDA(cudaMallocAsync((void**)&spec, (size_t)spec_slots * fx::SPEC_NODES * sizeof(fx::SpecEntry), s));
+  FX_CUDA(cudaMemsetAsync(scratch, 0, (SCR_WORDS + 8) * sizeof(unsigned long long), s));
+  FX_CUDA(cudaMemsetAsync(ring, 0, ring_words * sizeof(unsigned long long), s));
+  FX_CUDA(cudaMemsetAsync(bstate, 0, (size_t)n * sizeof(int2), s));
   int g = grid_for(n, 256, di.sms);
   count_models_kernel<<<g, 256, 0, s>>>(n, model_id, scratch);
   g_launches++;
   scatter_models_kernel<<<g, 256, 0, s>>>(n, model_id, scratch, perm, counters);
   g_launches++;
+  fx::init_queues_kernel<<<1, 32, 0, s>>>(scratch + SCR_COUNTS, ctl);
+  g_launches++;
   FX_CUDA(cudaGetLastError());
 
   fx::SolveArgs a;
   memset(&a, 0, sizeof a);
-  a.n = 0;
   a.counts = scratch + SCR_COUNTS;
   a.perm = perm;
   a.params = params;
@@ -383,7 +403,13 @@ int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, con
   a.counters = counters;
   a.knots = k_max > 0 ? knots : nullptr;
   a.k_max = k_max;
-  a.queue = scratch + SCR_QUEUES;
+  a.ctl = ctl;
+  a.ring = ring;
+  a.ring_pad = ring_pad;
+  a.bstate = bstate;
+  a.spec = spec;
+  a.spec_next = reinterpret_cast<unsigned int*>(scratch + SCR_WORDS);
+  a.spec_slots = (unsigned int)spec_slots;
   a.itol = o.itol;
   a.rtol = o.rtol;
   a.atol = o.atol;
@@ -406,6 +432,10 @@ int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, con
     FX_CUDA(cudaEventRecord(fk->done[m], fk->streams[m]));
     FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
   }
+  if (spec) FX_CUDA(cudaFreeAsync(spec, s));
+  FX_CUDA(cudaFreeAsync(bstate, s));
+  FX_CUDA(cudaFreeAsync(ring, s));
+  FX_CUDA(cudaFreeAsync(ctl, s));
   FX_CUDA(cudaFreeAsync(perm, s));
   FX_CUDA(cudaFreeAsync(scratch, s));
   return FX_OK;

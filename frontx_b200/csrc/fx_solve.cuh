@@ -1,4 +1,5 @@
-// fx_solve.cuh -- the batched shooting-solve kernel (one thread per problem).
+// fx_solve.cuh -- the batched shooting-solve kernel: persistent lanes, a device-wide queue
+// of SHOTS, speculative bisection when lanes would otherwise idle.
 //
 // Replaces, for a batch, the whole of frontx.solve (src/frontx/_forward.py:60-122):
 //   bisection on d_dob (optimistix.Bisection, :104-112)
@@ -7,29 +8,39 @@
 //         > 6 implicit stages, each a chord iteration on the 2-vector stage derivative
 //           > one right-hand side evaluation (src/frontx/_boltzmann.py:27-33)
 //
-// Design (B200, FP64-pipe bound; no tensor cores, nothing here is a contraction):
-//   * One thread owns one problem from first shot to converged bracket.  The
-//     five nested loops above are flattened into ONE loop whose trip is exactly
-//     one right-hand-side evaluation (D, D' -- and D'' on the trip that also
-//     builds the chord Jacobian).  Everything else (chord update, stage advance,
-//     error estimate / controller, event, bisection update, fetching the next
-//     problem) is a short predicated block after it, so lanes that are in
-//     different stages, steps, shots or problems still execute the expensive
-//     model evaluation convergently.
-//   * Persistent threads: a finished lane takes the next problem from a global
-//     counter (one atomicAdd per warp per trip at most), so a lane stuck in a
-//     4096-attempt crawl does not hold back its warp-mates' throughput.
-//   * The 7 stage derivatives live in shared memory, one column per thread
-//     (conflict-free), because the stage index is a per-lane runtime value; the
-//     Butcher tableau and predictor rows sit beside them.
-//   * Kernels are compiled per model (template parameter), so the model switch
-//     costs nothing and registers hold only that model's derived constants;
-//     mixed batches are bucketed by model on the device (fx_api.cu).
-//   * Output: 64-byte summary + 32-byte counter record per problem, and one
-//     32-byte knot (o, theta, theta', theta'') per accepted step.
-//   * The arithmetic itself is in fx_arith.cuh / fx_models.cuh / fx_math.cuh
-//     (host+device, explicit fma, built with -fmad=false) so that the CPU twin
-//     used by the tests reproduces every decision bit for bit.
+// Design (B200, FP64-pipe / issue bound; no tensor cores, nothing here is a contraction):
+//   * The unit of scheduling is ONE SHOT (an initial-value problem for one d_dob), not one
+//     problem.  A problem is ~18 sequential shots (102 when the bisection fails), a shot is
+//     ~1300 right-hand sides; at 10^5 problems per GPU there is barely more than one problem
+//     per resident lane, so problem-granular scheduling leaves a third of the lanes idle in
+//     a second round and the whole launch then waits for the 0.5 % of problems that need 5x
+//     the shots.  Here the bisection state of every problem lives in global memory (in the
+//     caller's own summary/counters rows plus 8 bytes of scratch) and lanes are workers: a
+//     lane pops a shot, integrates it, folds the residual into that problem's bisection,
+//     pushes the problem's next shot and pops the oldest waiting one (FIFO, so all problems
+//     advance at the same rate and finish together).
+//   * Speculative bisection: when fewer problems remain than lanes/3, the next 2..5 levels of
+//     a problem's bisection tree (3..31 midpoints, each a pure function of the bracket) are
+//     pushed as independent shots; whoever finishes the last of them walks the tree with the
+//     real residuals, consuming up to 5 bisection steps per round.  Results, counters and the
+//     accepted d_dob are identical to sequential bisection (only shots on the taken path are
+//     counted); the wasted shots run on lanes that had nothing else to do.  This is what
+//     shortens the critical path of the failing problems from ~55 sequential shots to ~25.
+//   * Inside a shot the four nested loops (step attempts > stages > chord iterations > RHS)
+//     are flattened into ONE loop whose trip is exactly one right-hand-side evaluation (D, D',
+//     1/D -- and D'' on the trip that also builds the chord Jacobian), so lanes in different
+//     stages, steps, shots or problems execute the expensive model evaluation convergently;
+//     everything else is a short predicated block after it.
+//   * The 7 stage derivatives live in shared memory, one column per thread (conflict-free),
+//     because the stage index is a per-lane runtime value; the Butcher tableau, predictor rows
+//     and the log/exp lookup tables sit beside them.
+//   * Kernels are compiled per model (template parameter); mixed batches are bucketed by
+//     model on the device (fx_api.cu) and each bucket has its own queue.
+//   * Output: 64-byte summary + 32-byte counter record per problem, and one 32-byte knot
+//     (o, theta, theta', theta'') per accepted step of the last shot.
+//   * The arithmetic itself is in fx_arith.cuh / fx_models.cuh / fx_math.cuh (host+device,
+//     explicit fma, built with -fmad=false) so that the CPU twin used by the tests reproduces
+//     every decision bit for bit, whatever order the queue ran the shots in.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -42,27 +53,89 @@
 namespace fx {
 
 constexpr int SOLVE_BLOCK = 128;
+constexpr int SPEC_MAX_DEPTH = 5;                // up to 31 speculative shots per problem
+constexpr int SPEC_NODES = 1 << SPEC_MAX_DEPTH;  // entries per speculation slot (entry 0 = header)
 
 __constant__ Tableau c_tab = FX_TABLEAU_INIT;
 
+// queue control block of one model bucket (set by init_queues_kernel)
+struct QueueCtl {
+  unsigned long long head;  // next ticket to hand out
+  unsigned long long tail;  // next ticket to reserve for a push (tickets >= n_work live in the ring)
+  long long avail;          // pushed and not yet claimed
+  long long remaining;      // unfinished problems
+  unsigned int abort;       // internal inconsistency (a ring entry never arrived): everyone leaves
+  unsigned int pad_[7];
+};
+
+// result of one shot: what the bisection and the counters need from it
+struct ShotResult {
+  double res, t_end, y_end;
+  int att, rej, rhs, knots;
+};
+
+// one node of a speculation slot (48 bytes, 16-byte aligned parts).  Entry 0 of a slot is
+// its header: k.x = shots of the batch still running, k.y = depth of the batch.
+struct SpecEntry {
+  int4 k;  // att, rej, rhs, knots
+  double res, t_end, y_end, pad_;
+};
+
 struct SolveArgs {
-  long long n;               // problems in this launch when counts == nullptr
-  const unsigned long long* counts;  // per-model bucket sizes (device), or nullptr
+  const unsigned long long* counts;  // per-model bucket sizes (device)
   int slot;                  // this launch's bucket
-  const int* perm;           // bucket-major list of problem indices, or nullptr
+  const int* perm;           // bucket-major list of problem indices
   const double* params;      // [N][12]
   const double* b;           // [N]
   const double* i;           // [N]
-  double* summary;           // [N][8]
-  int* counters;             // [N][8]
+  double* summary;           // [N][8]; rows double as bisection state while a problem is in flight
+  int* counters;             // [N][8]; likewise
   double* knots;             // [N][k_max][4] or nullptr
   int k_max;
-  unsigned long long* queue; // work counter (zeroed before launch)
+  QueueCtl* ctl;             // [8]
+  unsigned long long* ring;  // task ring shared by the buckets (each owns a region)
+  long long ring_pad;        // spare entries per bucket beyond its problem count
+  int2* bstate;              // [N]: .x = phase | lo_neg << 2 | n_bis << 3, .y = speculation slot + 1
+  SpecEntry* spec;           // [spec_slots][SPEC_NODES]
+  unsigned int* spec_next;   // bump allocator of speculation slots (shared by the buckets)
+  unsigned int spec_slots;
   double itol, rtol, atol, ob;
   int max_bisect, max_ode_steps, max_expansions, radial_k;
 };
 
 enum Mode : int { M_FETCH = 0, M_DB = 1, M_INIT0 = 2, M_INIT1 = 3, M_CHORD = 4, M_DONE = 5 };
+
+__device__ __forceinline__ unsigned long long ring_entry(int prob, int node, unsigned long long lap) {
+  return ((unsigned long long)((lap + 1) & 0xffffffull) << 40) | ((unsigned long long)(node & 0xff) << 32) |
+         (unsigned long long)(unsigned int)prob;
+}
+
+// push `count` shots of problem `prob` (nodes node0 .. node0+count-1) onto this bucket's ring.
+// The caller has made the problem's state visible (__threadfence) before calling.
+__device__ __forceinline__ void push_tasks(QueueCtl* ctl, unsigned long long* ring, long long n_work,
+                                           long long cap, int prob, int node0, int count) {
+  unsigned long long t = atomicAdd(&ctl->tail, (unsigned long long)count);
+  for (int k = 0; k < count; k++) {
+    unsigned long long r = t + k - (unsigned long long)n_work;
+    unsigned long long lap = r / (unsigned long long)cap, idx = r - lap * (unsigned long long)cap;
+    __stcg(&ring[idx], ring_entry(prob, node0 + k, lap));
+  }
+  __threadfence();
+  atomicAdd((unsigned long long*)&ctl->avail, (unsigned long long)count);
+}
+
+// midpoint of speculation node `node` (heap index, root 1) of the bracket [lower, upper]:
+// the same fma the sequential bisection evaluates after taking that path
+__device__ __forceinline__ double node_midpoint(double lower, double upper, int node) {
+  int depth = 31 - __clz(node);
+  double lo = lower, hi = upper;
+  double mid = fma(0.5, hi - lo, lo);
+  for (int l = depth - 1; l >= 0; l--) {
+    if ((node >> l) & 1) lo = mid; else hi = mid;
+    mid = fma(0.5, hi - lo, lo);
+  }
+  return mid;
+}
 
 template <int MODEL, bool RADIAL>
 __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveArgs A) {
@@ -87,67 +160,125 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
   const int radial_k = RADIAL ? A.radial_k : 0;
   auto fs = [&](int j, int c) -> double { return fsm[j][c][tid]; };
 
-  // bucket geometry: model `slot` owns perm[off .. off+n)
-  long long n_work = A.n;
-  const int* perm = A.perm;
-  unsigned long long* queue = A.queue;
-  if (A.counts) {
-    long long off = 0;
-    for (int k = 0; k < A.slot; k++) off += (long long)A.counts[k];
-    n_work = (long long)A.counts[A.slot];
-    perm += off;
-    queue += A.slot;
-  }
+  // bucket geometry: model `slot` owns perm[off .. off+n_work) and a ring region of its own
+  long long off = 0;
+  for (int k = 0; k < A.slot; k++) off += (long long)A.counts[k];
+  const long long n_work = (long long)A.counts[A.slot];
+  if (n_work == 0) return;
+  const int* perm = A.perm + off;
+  QueueCtl* ctl = A.ctl + A.slot;
+  unsigned long long* ring = A.ring + off + (long long)A.slot * A.ring_pad;
+  const long long ring_cap = n_work + A.ring_pad;
+  const long long n_lanes = (long long)gridDim.x * SOLVE_BLOCK;
+  const bool can_speculate = (A.knots == nullptr) && (A.spec_slots > 0);
 
   // ---- per-lane state ---------------------------------------------------
   int mode = M_FETCH;
-  long long prob = -1;
+  int prob = 0, node = 0;                  // the shot this lane is integrating
   double dpar[NDERIVED];
 #pragma unroll
   for (int k = 0; k < NDERIVED; k++) dpar[k] = 0.0;
-  double bnd_b = 0, bnd_i = 0, direction = 0, D_b = 0;
-  Bisect bis;
-  bis.start(1.0, 0.0, 0.0);
+  double bnd_b = 0, bnd_i = 0, direction = 0, d_shot = 0;
   double t0 = 0, t1 = 0, h = 0, y00 = 0, y01 = 0;  // step [t0,t1], h = t1 - t0, state at t0
   double yp0 = 0, yp1 = 0;                 // y_partial of the current stage
   double f0 = 0, f1 = 0;                   // chord iterate (stage derivative)
   Chord M = {0, 0, 0, 0};                  // inverse of gamma*h*J - I
   double dsz = 0;                          // square of the previous chord step size
   double te = 0, ye0 = 0, ye1 = 0;         // where the next RHS is evaluated
-  int stage = 1, iter = 0, att_shot = 0;
-  int n_shots = 0, n_att = 0, n_rej = 0, n_rhs = 0, n_jac = 0, n_knots = 0;
-  int rhs_mark = 0, rej_mark = 0;          // counters at the start of the current shot
+  int stage = 1, iter = 0;
+  int att_shot = 0, rej_shot = 0, rhs_shot = 0, n_knots = 0;
   double* knot_row = nullptr;
+  unsigned poll = 0;
 
   for (;;) {
-    // ---- fetch ----------------------------------------------------------
-    unsigned need = __ballot_sync(FULL, mode == M_FETCH);
-    if (need) {
-      int leader = __ffs(need) - 1;
-      unsigned long long base = 0;
-      if ((int)lane == leader) base = atomicAdd(queue, (unsigned long long)__popc(need));
-      base = __shfl_sync(FULL, base, leader);
-      if (mode == M_FETCH) {
-        long long w = (long long)base + __popc(need & ((1u << lane) - 1u));
-        if (w < n_work) {
-          prob = perm ? (long long)perm[w] : w;
-          const double* p = A.params + prob * FX_NPARAM;
-          derive_params<MODEL>(p, dpar, mt);
-          bnd_b = A.b[prob];
-          bnd_i = A.i[prob];
-          direction = (bnd_i > bnd_b) ? 1.0 : ((bnd_i < bnd_b) ? -1.0 : 0.0);
-          knot_row = A.knots ? A.knots + (size_t)prob * A.k_max * FX_KNOT : nullptr;
-          n_shots = n_att = n_rej = n_rhs = n_jac = n_knots = 0;
-          mode = M_DB;
-          te = A.ob;
-          ye0 = bnd_b;
-          ye1 = 0.0;
-        } else {
-          mode = M_DONE;
+    // ---- fetch: pop shots for the lanes that have none -------------------------------------
+    const unsigned need = __ballot_sync(FULL, mode == M_FETCH);
+    const bool busy = __any_sync(FULL, mode != M_FETCH && mode != M_DONE);
+    if (need && (!busy || (poll++ & 7u) == 0)) {
+      const int leader = __ffs(need) - 1;
+      const int want = __popc(need);
+      long long got = 0;
+      unsigned long long h0 = 0;
+      if ((int)lane == leader) {
+        const long long rem = *(volatile long long*)&ctl->remaining;
+        const unsigned int ab = *(volatile unsigned int*)&ctl->abort;
+        if (rem <= 0 || ab) {
+          got = -1;
+        } else if (*(volatile long long*)&ctl->avail > 0) {
+          long long old = (long long)atomicAdd((unsigned long long*)&ctl->avail,
+                                               (unsigned long long)(-(long long)want));
+          got = old >= want ? want : (old > 0 ? old : 0);
+          if (got < want) atomicAdd((unsigned long long*)&ctl->avail, (unsigned long long)(want - got));
+          if (got > 0) h0 = atomicAdd(&ctl->head, (unsigned long long)got);
         }
       }
+      got = __shfl_sync(FULL, got, leader);
+      h0 = __shfl_sync(FULL, h0, leader);
+      if (mode == M_FETCH) {
+        const int rank = __popc(need & ((1u << lane) - 1u));
+        if (got < 0) {
+          mode = M_DONE;
+        } else if (rank < got) {
+          const unsigned long long ticket = h0 + rank;
+          const bool fresh = ticket < (unsigned long long)n_work;
+          bool lost = false;
+          if (fresh) {
+            prob = perm[ticket];
+            node = 0;
+          } else {
+            unsigned long long r = ticket - (unsigned long long)n_work;
+            unsigned long long lap = r / (unsigned long long)ring_cap, idx = r - lap * (unsigned long long)ring_cap;
+            const unsigned long long seq = (lap + 1) & 0xffffffull;
+            unsigned long long e = __ldcg(&ring[idx]);
+            unsigned spins = 0;
+            while ((e >> 40) != seq) {
+              __nanosleep(64);
+              e = __ldcg(&ring[idx]);
+              if (++spins > (1u << 22)) {  // the matching push never arrived: give up loudly
+                atomicExch(&ctl->abort, 1u);
+                lost = true;
+                break;
+              }
+            }
+            __threadfence();
+            prob = (int)(unsigned int)(e & 0xffffffffull);
+            node = (int)((e >> 32) & 0xff);
+          }
+          if (lost) {
+            mode = M_DONE;
+          } else {
+            const double* p = A.params + (size_t)prob * FX_NPARAM;
+            derive_params<MODEL>(p, dpar, mt);
+            bnd_b = A.b[prob];
+            bnd_i = A.i[prob];
+            direction = (bnd_i > bnd_b) ? 1.0 : ((bnd_i < bnd_b) ? -1.0 : 0.0);
+            knot_row = A.knots ? A.knots + (size_t)prob * A.k_max * FX_KNOT : nullptr;
+            if (fresh) {
+              mode = M_DB;  // D(b) first: the bracket needs it
+              te = A.ob;
+              ye0 = bnd_b;
+              ye1 = 0.0;
+            } else {
+              const double* S = A.summary + (size_t)prob * FX_NSUM;
+              const double lower = __ldcg(S + 6), upper = __ldcg(S + 7);
+              const int phase = __ldcg(&A.bstate[prob].x) & 3;
+              d_shot = (phase == 0) ? lower : (phase == 1) ? upper : node_midpoint(lower, upper, node ? node : 1);
+              t0 = A.ob;
+              y00 = bnd_b;
+              y01 = d_shot;
+              att_shot = rej_shot = rhs_shot = 0;
+              te = t0;
+              ye0 = y00;
+              ye1 = y01;
+              mode = M_INIT0;
+            }
+          }
+        }
+      }
+      if (!busy && got == 0) __nanosleep(2000);
     }
     if (!__any_sync(FULL, mode != M_DONE)) break;
+    if (!__any_sync(FULL, mode != M_FETCH && mode != M_DONE)) continue;
 
     // ---- the one expensive thing per trip: a right-hand-side evaluation ---
     const bool wantJ = (mode == M_CHORD) && (stage == 1) && (iter == 0);
@@ -156,18 +287,36 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
     const Rhs R = rhs_eval(D1, iD, te, ye1, radial_k);
 
     bool att_end = false, att_ok = false, shot_end = false, occurred = false;
-    bool start_shot = false, prep = false;
+    bool prep = false;
 
     if (mode == M_DB) {
-      D_b = D;
+      // fresh problem: bracket [0, (i-b)/(2 sqrt(D(b)))], first shot at its lower end
+      Bisect bis;
       bis.start(D, bnd_b, bnd_i);
-      start_shot = true;
+      double* S = A.summary + (size_t)prob * FX_NSUM;
+      __stcg(S + 4, D);
+      __stcg(S + 6, bis.lower);
+      __stcg(S + 7, bis.upper);
+      int4* c = reinterpret_cast<int4*>(A.counters + (size_t)prob * FX_NCNT);
+      __stcg(c, make_int4(0, 0, 0, 0));
+      __stcg(c + 1, make_int4(0, 0, 0, 0));
+      __stcg(&A.bstate[prob], make_int2(0, 0));
+      d_shot = bis.lower;
+      t0 = A.ob;
+      y00 = bnd_b;
+      y01 = d_shot;
+      att_shot = rej_shot = rhs_shot = 0;
+      te = t0;
+      ye0 = y00;
+      ye1 = y01;
+      mode = M_INIT0;
     } else if (mode == M_INIT0) {
       // solver.init + first half of the Hairer initial-step heuristic
-      n_rhs++;
+      rhs_shot++;
       fsm[0][0][tid] = R.F0;
       fsm[0][1][tid] = R.F1;
-      if (knot_row && A.k_max > 0) *reinterpret_cast<double4*>(knot_row) = make_double4(t0, y00, y01, R.F1);
+      if (knot_row && node == 0 && A.k_max > 0)
+        *reinterpret_cast<double4*>(knot_row) = make_double4(t0, y00, y01, R.F1);
       n_knots = 1;
       double h0, d1;
       init_h0(y00, y01, R.F0, R.F1, tol, h0, d1);
@@ -178,7 +327,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       ye1 = fma(h0, R.F1, y01);
       mode = M_INIT1;
     } else if (mode == M_INIT1) {
-      n_rhs++;
+      rhs_shot++;
       double dt = init_dt(y00, y01, fs(0, 0), fs(0, 1), R.F0, R.F1, h, dsz, tol, mt);
       t1 = t0 + dt;
       h = t1 - t0;
@@ -186,11 +335,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       prep = true;
       mode = M_CHORD;
     } else if (mode == M_CHORD) {
-      n_rhs++;
-      if (wantJ) {
-        n_jac++;
-        M = chord_matrix(D, D1, D2, R, te, ye1, h, radial_k);
-      }
+      rhs_shot++;
+      if (wantJ) M = chord_matrix(D, D1, D2, R, te, ye1, h, radial_k);
       double size = chord_update(M, R.F0, R.F1, f0, f1, tol);
       iter++;
       bool done, ok;
@@ -213,7 +359,6 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
 
     // ---- end of a step attempt: error estimate, controller, event ---------
     if (att_end) {
-      n_att++;
       att_shot++;
       StepEnd s = step_finish(tab, att_ok, fs, y00, y01, yp0, yp1, f0, f1, h, tol, mt);
       if (s.keep) {
@@ -222,7 +367,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
         y01 = s.y11;
         fsm[0][0][tid] = f0;  // FSAL
         fsm[0][1][tid] = f1;
-        if (knot_row && n_knots < A.k_max) {
+        if (knot_row && node == 0 && n_knots < A.k_max) {
           double4* dst = reinterpret_cast<double4*>(knot_row + (size_t)n_knots * FX_KNOT);
           *dst = make_double4(t0, y00, y01, f1);
         }
@@ -232,7 +377,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
           occurred = true;
         }
       } else {
-        n_rej++;
+        rej_shot++;
       }
       if (!shot_end) {
         if (att_shot >= A.max_ode_steps) {
@@ -246,51 +391,112 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       }
     }
 
-    // ---- end of a shot: residual, bisection bookkeeping --------------------
+    // ---- end of a shot: fold it into the problem's bisection ----------------
     if (shot_end) {
-      double res = occurred ? (y00 - bnd_i) : direction * fx_inf();  // _forward.py:97-101
-      n_shots++;
-      double d_shot = bis.d_cur;
-      const int rhs_shot = n_rhs - rhs_mark, rej_shot = n_rej - rej_mark;
-      int result = bis.next(res, A.itol, A.max_bisect, A.max_expansions);
-      // A shot is a pure function of d_dob.  Once the bracket has collapsed to two adjacent
-      // doubles without |res| < itol, the midpoint is one of its ends and every remaining
-      // bisection step repeats the shot just made: replay its residual and counters
-      // instead of integrating again (the knot row it wrote is the same too).
-      while (result < 0 && bis.d_cur == d_shot) {
-        n_shots++;
-        n_att += att_shot;
-        n_rej += rej_shot;
-        n_rhs += rhs_shot;
-        n_jac += att_shot;
-        result = bis.next(res, A.itol, A.max_bisect, A.max_expansions);
+      const double res = occurred ? (y00 - bnd_i) : direction * fx_inf();  // _forward.py:97-101
+      double* S = A.summary + (size_t)prob * FX_NSUM;
+      int4* C = reinterpret_cast<int4*>(A.counters + (size_t)prob * FX_NCNT);
+      int2 bs = __ldcg(&A.bstate[prob]);
+      SpecEntry* slot = (node > 0) ? A.spec + (size_t)(bs.y - 1) * SPEC_NODES : nullptr;
+      bool walker = true;
+      int depth = 1;
+      if (node > 0) {
+        // one of a speculative batch: record the result; the lane that completes the batch walks it
+        SpecEntry* e = slot + node;
+        __stcg(&e->k, make_int4(att_shot, rej_shot, rhs_shot, n_knots));
+        __stcg(&e->res, res);
+        __stcg(&e->t_end, t0);
+        __stcg(&e->y_end, y00);
+        depth = __ldcg(&slot->k.y);
+        __threadfence();
+        walker = atomicSub(&slot->k.x, 1) == 1;
+        if (walker) __threadfence();
       }
-      if (result < 0) {
-        start_shot = true;
-      } else {
-        double2* s = reinterpret_cast<double2*>(A.summary + (size_t)prob * FX_NSUM);
-        s[0] = make_double2(d_shot, t0);
-        s[1] = make_double2(y00, -2.0 * D_b * d_shot);
-        s[2] = make_double2(D_b, res);
-        s[3] = make_double2(bis.lower, bis.upper);
-        int4* c = reinterpret_cast<int4*>(A.counters + (size_t)prob * FX_NCNT);
-        c[0] = make_int4(result, n_shots, bis.n_exp, n_att);
-        c[1] = make_int4(n_rej, n_rhs, n_jac, n_knots);
-        mode = M_FETCH;
+      if (walker) {
+        Bisect bis;
+        bis.lower = __ldcg(S + 6);
+        bis.upper = __ldcg(S + 7);
+        const double D_b = __ldcg(S + 4);
+        const int4 c0 = __ldcg(C), c1 = __ldcg(C + 1);
+        bis.phase = bs.x & 3;
+        bis.lo_neg = (bs.x >> 2) & 1;
+        bis.n_bis = bs.x >> 3;
+        bis.n_exp = c0.z;
+        int n_shots = c0.y, n_att = c0.w, n_rej = c1.x, n_rhs = c1.y;
+        int cur = node > 0 ? 1 : 0;  // tree node being consumed (0: the ordinary single shot)
+        bis.d_cur = (node > 0) ? node_midpoint(bis.lower, bis.upper, 1) : d_shot;
+        ShotResult e = {res, t0, y00, att_shot, rej_shot, rhs_shot, n_knots};
+        int result = -1;
+        double d_last = d_shot;
+        for (int level = 0;; level++) {
+          if (node > 0) {
+            if (cur != node) {
+              const SpecEntry* q = slot + cur;
+              const int4 k = __ldcg(&q->k);
+              e.res = __ldcg(&q->res);
+              e.t_end = __ldcg(&q->t_end);
+              e.y_end = __ldcg(&q->y_end);
+              e.att = k.x; e.rej = k.y; e.rhs = k.z; e.knots = k.w;
+            } else {
+              e = ShotResult{res, t0, y00, att_shot, rej_shot, rhs_shot, n_knots};
+            }
+          }
+          d_last = bis.d_cur;
+          const bool went_right = ((e.res < 0.0) == (bool)bis.lo_neg);
+          n_shots++;
+          n_att += e.att;
+          n_rej += e.rej;
+          n_rhs += e.rhs;
+          result = bis.next(e.res, A.itol, A.max_bisect, A.max_expansions);
+          // A shot is a pure function of d_dob.  Once the bracket has collapsed to two adjacent
+          // doubles without |res| < itol, the midpoint is one of its ends and every remaining
+          // bisection step repeats the shot just made: replay its residual and counters.
+          while (result < 0 && bis.d_cur == d_last) {
+            n_shots++;
+            n_att += e.att;
+            n_rej += e.rej;
+            n_rhs += e.rhs;
+            result = bis.next(e.res, A.itol, A.max_bisect, A.max_expansions);
+          }
+          if (result >= 0 || level + 1 >= depth) break;
+          cur = 2 * cur + (went_right ? 1 : 0);
+        }
+        if (result >= 0) {
+          double2* s2 = reinterpret_cast<double2*>(S);
+          __stcg(s2 + 0, make_double2(d_last, e.t_end));
+          __stcg(s2 + 1, make_double2(e.y_end, -2.0 * D_b * d_last));
+          __stcg(s2 + 2, make_double2(D_b, e.res));
+          __stcg(s2 + 3, make_double2(bis.lower, bis.upper));
+          __stcg(C, make_int4(result, n_shots, bis.n_exp, n_att));
+          __stcg(C + 1, make_int4(n_rej, n_rhs, n_att, e.knots));
+          atomicAdd((unsigned long long*)&ctl->remaining, (unsigned long long)(-1LL));
+        } else {
+          // not converged: save the bisection state and queue the problem's next shot(s)
+          __stcg(S + 6, bis.lower);
+          __stcg(S + 7, bis.upper);
+          __stcg(C, make_int4(0, n_shots, bis.n_exp, n_att));
+          __stcg(C + 1, make_int4(n_rej, n_rhs, n_att, e.knots));
+          int d = 1;
+          if (can_speculate && bis.phase == 2) {
+            const long long rem = *(volatile long long*)&ctl->remaining;
+            while (d < SPEC_MAX_DEPTH && rem * ((2LL << d) - 1) <= n_lanes) d++;
+            if (d > 1 && bs.y == 0) {
+              unsigned int sl = atomicAdd(A.spec_next, 1u);
+              if (sl < A.spec_slots) bs.y = (int)sl + 1; else d = 1;
+            }
+          }
+          bs.x = bis.phase | (bis.lo_neg << 2) | (bis.n_bis << 3);
+          __stcg(&A.bstate[prob], bs);
+          if (d > 1) {
+            SpecEntry* hdr = A.spec + (size_t)(bs.y - 1) * SPEC_NODES;
+            __stcg(&hdr->k, make_int4((1 << d) - 1, d, 0, 0));
+          }
+          __threadfence();
+          if (d > 1) push_tasks(ctl, ring, n_work, ring_cap, prob, 1, (1 << d) - 1);
+          else push_tasks(ctl, ring, n_work, ring_cap, prob, 0, 1);
+        }
       }
-    }
-
-    if (start_shot) {
-      t0 = A.ob;
-      y00 = bnd_b;
-      y01 = bis.d_cur;
-      att_shot = 0;
-      rhs_mark = n_rhs;
-      rej_mark = n_rej;
-      te = t0;
-      ye0 = y00;
-      ye1 = y01;
-      mode = M_INIT0;
+      mode = M_FETCH;
     }
 
     // ---- set up an implicit stage: y_partial, predictor, node --------------
@@ -300,6 +506,19 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       ye0 = stage_point(yp0, h, f0);
       ye1 = stage_point(yp1, h, f1);
     }
+  }
+}
+
+// sets each bucket's queue control block from the bucket sizes (one thread per bucket)
+__global__ void init_queues_kernel(const unsigned long long* counts, QueueCtl* ctl) {
+  int m = threadIdx.x;
+  if (m < 8) {
+    long long n = (long long)counts[m];
+    ctl[m].head = 0;
+    ctl[m].tail = (unsigned long long)n;
+    ctl[m].avail = n;
+    ctl[m].remaining = n;
+    ctl[m].abort = 0;
   }
 }
 
