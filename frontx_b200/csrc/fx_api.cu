@@ -364,7 +364,7 @@ int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, con
   const long long max_lanes = (long long)di.sms * 2048;
   const long long ring_pad = max_lanes + 64;
   const size_t ring_words = (size_t)n + 8 * (size_t)ring_pad;
-  long long spec_slots = max_lanes / 3 + 8;
+  long long spec_slots = (long long)di.sms * 512 + 8;  // >= resident lanes at 128 registers/thread
   if (spec_slots > n) spec_slots = n;
   if (k_max > 0) spec_slots = 0;  // dense output requested: the last shot must write its knots itself
   unsigned long long* scratch = nullptr;

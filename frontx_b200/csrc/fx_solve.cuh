@@ -53,6 +53,7 @@
 namespace fx {
 
 constexpr int SOLVE_BLOCK = 128;
+constexpr int SOLVE_CTAS_PER_SM = 4;             // 128 registers per thread: 4 warps per SM sub-partition
 constexpr int SPEC_MAX_DEPTH = 5;                // up to 31 speculative shots per problem
 constexpr int SPEC_NODES = 1 << SPEC_MAX_DEPTH;  // entries per speculation slot (entry 0 = header)
 
@@ -138,7 +139,7 @@ __device__ __forceinline__ double node_midpoint(double lower, double upper, int 
 }
 
 template <int MODEL, bool RADIAL>
-__global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveArgs A) {
+__global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_kernel(const SolveArgs A) {
   __shared__ Tableau tab;
   __shared__ MathTab mt;                     // log / exp lookup tables (lanes index them divergently)
   __shared__ double fsm[7][2][SOLVE_BLOCK];  // stage derivatives, one column per thread
@@ -188,20 +189,28 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
   int stage = 1, iter = 0;
   int att_shot = 0, rej_shot = 0, rhs_shot = 0, n_knots = 0;
   double* knot_row = nullptr;
-  unsigned poll = 0;
+  unsigned poll = 0, idle_ns = 1000u;
+  bool sparse = false;                     // few problems left: spread shots over warps
 
   for (;;) {
     // ---- fetch: pop shots for the lanes that have none -------------------------------------
     const unsigned need = __ballot_sync(FULL, mode == M_FETCH);
     const bool busy = __any_sync(FULL, mode != M_FETCH && mode != M_DONE);
-    if (need && (!busy || (poll++ & 7u) == 0)) {
+    // A warp that is already integrating takes new shots into its free lanes at no issue cost,
+    // so it polls often; a fully idle warp backs off (1 -> 16 us), which makes late, sparse
+    // work settle into few full warps instead of many nearly empty ones.
+    // In the last rounds (few problems left, each a critical path) the opposite holds: a shot
+    // runs fastest in a warp of its own, so busy warps stop taking work and idle ones poll fast.
+    if (need && (!busy || (poll++ & (sparse ? 15u : 1u)) == 0)) {
       const int leader = __ffs(need) - 1;
       const int want = __popc(need);
       long long got = 0;
       unsigned long long h0 = 0;
+      bool sparse_now = false;
       if ((int)lane == leader) {
         const long long rem = *(volatile long long*)&ctl->remaining;
         const unsigned int ab = *(volatile unsigned int*)&ctl->abort;
+        sparse_now = rem * 16 < n_lanes;
         if (rem <= 0 || ab) {
           got = -1;
         } else if (*(volatile long long*)&ctl->avail > 0) {
@@ -214,6 +223,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
       }
       got = __shfl_sync(FULL, got, leader);
       h0 = __shfl_sync(FULL, h0, leader);
+      sparse = __shfl_sync(FULL, (int)sparse_now, leader) != 0;
       if (mode == M_FETCH) {
         const int rank = __popc(need & ((1u << lane) - 1u));
         if (got < 0) {
@@ -275,7 +285,14 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
           }
         }
       }
-      if (!busy && got == 0) __nanosleep(2000);
+      if (!busy) {
+        if (got == 0) {
+          __nanosleep(sparse ? 500u : idle_ns);
+          if (idle_ns < 16000u) idle_ns *= 2;
+        } else {
+          idle_ns = 1000u;
+        }
+      }
     }
     if (!__any_sync(FULL, mode != M_DONE)) break;
     if (!__any_sync(FULL, mode != M_FETCH && mode != M_DONE)) continue;
@@ -465,6 +482,13 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
           double2* s2 = reinterpret_cast<double2*>(S);
           __stcg(s2 + 0, make_double2(d_last, e.t_end));
           __stcg(s2 + 1, make_double2(e.y_end, -2.0 * D_b * d_last));
+#ifdef FX_DEBUG_TIMES
+          {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            e.res = (double)now;  // developer experiment: finish time in the residual slot
+          }
+#endif
           __stcg(s2 + 2, make_double2(D_b, e.res));
           __stcg(s2 + 3, make_double2(bis.lower, bis.upper));
           __stcg(C, make_int4(result, n_shots, bis.n_exp, n_att));
@@ -476,10 +500,21 @@ __global__ void __launch_bounds__(SOLVE_BLOCK) shoot_bisect_kernel(const SolveAr
           __stcg(S + 7, bis.upper);
           __stcg(C, make_int4(0, n_shots, bis.n_exp, n_att));
           __stcg(C + 1, make_int4(n_rej, n_rhs, n_att, e.knots));
+          // Speculation depth: batches of 2^d - 1 shots, sized so that the batches of all
+          // unfinished problems together fill the resident lanes (rho = lanes per problem);
+          // the fractional level is rounded per problem and shot by a hash, which keeps the
+          // choice a pure function of (problem, shot, problems remaining).
           int d = 1;
           if (can_speculate && bis.phase == 2) {
-            const long long rem = *(volatile long long*)&ctl->remaining;
-            while (d < SPEC_MAX_DEPTH && rem * ((2LL << d) - 1) <= n_lanes) d++;
+            long long rem = *(volatile long long*)&ctl->remaining;
+            if (rem < 1) rem = 1;
+            const long long rho = n_lanes * 256 / rem;  // lanes per unfinished problem, in 1/256
+            while (d < SPEC_MAX_DEPTH && ((2LL << d) - 1) * 256 <= rho) d++;
+            if (d < SPEC_MAX_DEPTH) {
+              const long long lo = ((1LL << d) - 1) * 256, hi = ((2LL << d) - 1) * 256;
+              const unsigned u = (((unsigned)prob * 2654435761u) ^ ((unsigned)n_shots * 40503u)) >> 24;
+              if ((rho - lo) * 256 > (hi - lo) * (long long)u) d++;
+            }
             if (d > 1 && bs.y == 0) {
               unsigned int sl = atomicAdd(A.spec_next, 1u);
               if (sl < A.spec_slots) bs.y = (int)sl + 1; else d = 1;

@@ -42,8 +42,8 @@ ok = cnt[:, 0] == 0
 print(f"all {N}: {t_all:.1f} ms; failing {int((~ok).sum())}; rhs mean {cnt[:,5].mean():.0f} max {cnt[:,5].max()}")
 t_ok, _ = run(models.model_id[ok], models.params[ok])
 print(f"successes only ({int(ok.sum())}): {t_ok:.1f} ms")
-for n in (148 * 128 * 2, 148 * 128 * 4, 148 * 128 * 8):
-    idx = np.where(ok)[0][:n]
-    t, c = run(models.model_id[idx], models.params[idx])
-    print(f"successes, n = {n} ({n / (148 * 4 * 32):.1f} warps/SMSP of work): {t:.1f} ms -> {n / t * 1e3:.0f} solves/s; "
+big = bench.c2_workload(400_000, seed=5)
+for n in (148 * 128 * 2, 148 * 128 * 4, 148 * 128 * 8, 148 * 128 * 16):
+    t, c = run(big.model_id[:n], big.params[:n], reps=2)
+    print(f"n = {n} ({n / (148 * 4 * 32):.1f} warps/SMSP of work): {t:.1f} ms -> {n / t * 1e3:.0f} solves/s; "
           f"rhs mean {c[:,5].mean():.0f} max {c[:,5].max()}")
