@@ -104,12 +104,18 @@ int launch_model(const fx::SolveArgs& a, bool radial, int grid, cudaStream_t s) 
 
 template <int MODEL>
 int occupancy_of(bool radial, int* blocks) {
-  if (radial)
+  // the kernel keeps its per-lane state in shared memory: ask for the largest carve-out
+  if (radial) {
+    FX_CUDA(cudaFuncSetAttribute(fx::shoot_bisect_kernel<MODEL, true>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         blocks, fx::shoot_bisect_kernel<MODEL, true>, fx::SOLVE_BLOCK, 0));
-  else
+  } else {
+    FX_CUDA(cudaFuncSetAttribute(fx::shoot_bisect_kernel<MODEL, false>,
+                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         blocks, fx::shoot_bisect_kernel<MODEL, false>, fx::SOLVE_BLOCK, 0));
+  }
   return FX_OK;
 }
 

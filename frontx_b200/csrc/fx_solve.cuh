@@ -53,7 +53,7 @@
 namespace fx {
 
 constexpr int SOLVE_BLOCK = 128;
-constexpr int SOLVE_CTAS_PER_SM = 4;             // 128 registers per thread: 4 warps per SM sub-partition
+constexpr int SOLVE_CTAS_PER_SM = 5;             // 128 registers per thread: 4 warps per SM sub-partition
 constexpr int SPEC_MAX_DEPTH = 5;                // up to 31 speculative shots per problem
 constexpr int SPEC_NODES = 1 << SPEC_MAX_DEPTH;  // entries per speculation slot (entry 0 = header)
 
@@ -138,11 +138,34 @@ __device__ __forceinline__ double node_midpoint(double lower, double upper, int 
   return mid;
 }
 
+// derived constants actually used by each model (rows of s_dpar)
+template <int MODEL>
+struct DerivedCount {
+  static constexpr int value = MODEL == FX_CONSTANT ? 2 : MODEL == FX_POWER_LAW ? 4 : MODEL == FX_LOG ? 2 :
+                               MODEL == FX_BROOKS_COREY ? 6 : MODEL == FX_VAN_GENUCHTEN ? 8 :
+                               MODEL == FX_LETD ? 8 : 11;
+};
+
+struct BlockCtx {
+  long long n_work, ring_cap, n_lanes;
+  const int* perm;
+  QueueCtl* ctl;
+  unsigned long long* ring;
+};
+
 template <int MODEL, bool RADIAL>
 __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_kernel(const SolveArgs A) {
+  constexpr int NDP = DerivedCount<MODEL>::value;
   __shared__ Tableau tab;
   __shared__ MathTab mt;                     // log / exp lookup tables (lanes index them divergently)
   __shared__ double fsm[7][2][SOLVE_BLOCK];  // stage derivatives, one column per thread
+  // Per-lane state that is not needed on every trip lives in shared memory (one column per
+  // thread, conflict-free) so that the registers hold only the hot integrator state:
+  // registers, not arithmetic, bound the resident warps of this kernel.
+  __shared__ double s_dpar[NDP][SOLVE_BLOCK];  // the model's derived constants
+  __shared__ double s_cold[5][SOLVE_BLOCK];    // b, i, direction, d_dob of the shot, t1
+  __shared__ int s_cnt[3][SOLVE_BLOCK];        // attempts, rejections, knots of the shot
+  __shared__ BlockCtx ctx;                     // bucket geometry (same for every thread)
 
   const int tid = threadIdx.x;
   {
@@ -162,35 +185,41 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
   auto fs = [&](int j, int c) -> double { return fsm[j][c][tid]; };
 
   // bucket geometry: model `slot` owns perm[off .. off+n_work) and a ring region of its own
-  long long off = 0;
-  for (int k = 0; k < A.slot; k++) off += (long long)A.counts[k];
-  const long long n_work = (long long)A.counts[A.slot];
-  if (n_work == 0) return;
-  const int* perm = A.perm + off;
-  QueueCtl* ctl = A.ctl + A.slot;
-  unsigned long long* ring = A.ring + off + (long long)A.slot * A.ring_pad;
-  const long long ring_cap = n_work + A.ring_pad;
-  const long long n_lanes = (long long)gridDim.x * SOLVE_BLOCK;
+  if (tid == 0) {
+    long long off = 0;
+    for (int k = 0; k < A.slot; k++) off += (long long)A.counts[k];
+    ctx.n_work = (long long)A.counts[A.slot];
+    ctx.perm = A.perm + off;
+    ctx.ctl = A.ctl + A.slot;
+    ctx.ring = A.ring + off + (long long)A.slot * A.ring_pad;
+    ctx.ring_cap = ctx.n_work + A.ring_pad;
+    ctx.n_lanes = (long long)gridDim.x * SOLVE_BLOCK;
+  }
+  __syncthreads();
+  if (ctx.n_work == 0) return;
   const bool can_speculate = (A.knots == nullptr) && (A.spec_slots > 0);
 
-  // ---- per-lane state ---------------------------------------------------
+  // ---- per-lane state (registers) ---------------------------------------
   int mode = M_FETCH;
   int prob = 0, node = 0;                  // the shot this lane is integrating
-  double dpar[NDERIVED];
-#pragma unroll
-  for (int k = 0; k < NDERIVED; k++) dpar[k] = 0.0;
-  double bnd_b = 0, bnd_i = 0, direction = 0, d_shot = 0;
-  double t0 = 0, t1 = 0, h = 0, y00 = 0, y01 = 0;  // step [t0,t1], h = t1 - t0, state at t0
+  double t0 = 0, h = 0, y00 = 0, y01 = 0;  // step [t0,t1], h = t1 - t0, state at t0
   double yp0 = 0, yp1 = 0;                 // y_partial of the current stage
   double f0 = 0, f1 = 0;                   // chord iterate (stage derivative)
   Chord M = {0, 0, 0, 0};                  // inverse of gamma*h*J - I
   double dsz = 0;                          // square of the previous chord step size
   double te = 0, ye0 = 0, ye1 = 0;         // where the next RHS is evaluated
-  int stage = 1, iter = 0;
-  int att_shot = 0, rej_shot = 0, rhs_shot = 0, n_knots = 0;
-  double* knot_row = nullptr;
+  int stage = 1, iter = 0, rhs_shot = 0;
   unsigned poll = 0, idle_ns = 1000u;
   bool sparse = false;                     // few problems left: spread shots over warps
+  // ---- per-lane state (shared memory columns) ----------------------------
+  double& bnd_b = s_cold[0][tid];
+  double& bnd_i = s_cold[1][tid];
+  double& direction = s_cold[2][tid];
+  double& d_shot = s_cold[3][tid];
+  double& t1 = s_cold[4][tid];
+  int& att_shot = s_cnt[0][tid];
+  int& rej_shot = s_cnt[1][tid];
+  int& n_knots = s_cnt[2][tid];
 
   for (;;) {
     // ---- fetch: pop shots for the lanes that have none -------------------------------------
@@ -208,9 +237,10 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       unsigned long long h0 = 0;
       bool sparse_now = false;
       if ((int)lane == leader) {
+        QueueCtl* ctl = ctx.ctl;
         const long long rem = *(volatile long long*)&ctl->remaining;
         const unsigned int ab = *(volatile unsigned int*)&ctl->abort;
-        sparse_now = rem * 16 < n_lanes;
+        sparse_now = rem * 16 < ctx.n_lanes;
         if (rem <= 0 || ab) {
           got = -1;
         } else if (*(volatile long long*)&ctl->avail > 0) {
@@ -230,14 +260,16 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
           mode = M_DONE;
         } else if (rank < got) {
           const unsigned long long ticket = h0 + rank;
-          const bool fresh = ticket < (unsigned long long)n_work;
+          const bool fresh = ticket < (unsigned long long)ctx.n_work;
           bool lost = false;
           if (fresh) {
-            prob = perm[ticket];
+            prob = ctx.perm[ticket];
             node = 0;
           } else {
-            unsigned long long r = ticket - (unsigned long long)n_work;
-            unsigned long long lap = r / (unsigned long long)ring_cap, idx = r - lap * (unsigned long long)ring_cap;
+            const unsigned long long* ring = ctx.ring;
+            const unsigned long long ring_cap = (unsigned long long)ctx.ring_cap;
+            unsigned long long r = ticket - (unsigned long long)ctx.n_work;
+            unsigned long long lap = r / ring_cap, idx = r - lap * ring_cap;
             const unsigned long long seq = (lap + 1) & 0xffffffull;
             unsigned long long e = __ldcg(&ring[idx]);
             unsigned spins = 0;
@@ -245,7 +277,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
               __nanosleep(64);
               e = __ldcg(&ring[idx]);
               if (++spins > (1u << 22)) {  // the matching push never arrived: give up loudly
-                atomicExch(&ctl->abort, 1u);
+                atomicExch(&ctx.ctl->abort, 1u);
                 lost = true;
                 break;
               }
@@ -257,12 +289,15 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
           if (lost) {
             mode = M_DONE;
           } else {
-            const double* p = A.params + (size_t)prob * FX_NPARAM;
-            derive_params<MODEL>(p, dpar, mt);
+            {
+              double dpar[NDERIVED];
+              derive_params<MODEL>(A.params + (size_t)prob * FX_NPARAM, dpar, mt);
+#pragma unroll
+              for (int k = 0; k < NDP; k++) s_dpar[k][tid] = dpar[k];
+            }
             bnd_b = A.b[prob];
             bnd_i = A.i[prob];
             direction = (bnd_i > bnd_b) ? 1.0 : ((bnd_i < bnd_b) ? -1.0 : 0.0);
-            knot_row = A.knots ? A.knots + (size_t)prob * A.k_max * FX_KNOT : nullptr;
             if (fresh) {
               mode = M_DB;  // D(b) first: the bracket needs it
               te = A.ob;
@@ -300,7 +335,12 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     // ---- the one expensive thing per trip: a right-hand-side evaluation ---
     const bool wantJ = (mode == M_CHORD) && (stage == 1) && (iter == 0);
     double D, D1, D2, iD;
-    eval_D<MODEL>(dpar, ye0, wantJ, D, D1, D2, iD, mt);
+    {
+      double dpar[NDERIVED];
+#pragma unroll
+      for (int k = 0; k < NDERIVED; k++) dpar[k] = (k < NDP) ? s_dpar[k < NDP ? k : 0][tid] : 0.0;
+      eval_D<MODEL>(dpar, ye0, wantJ, D, D1, D2, iD, mt);
+    }
     const Rhs R = rhs_eval(D1, iD, te, ye1, radial_k);
 
     bool att_end = false, att_ok = false, shot_end = false, occurred = false;
@@ -332,8 +372,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       rhs_shot++;
       fsm[0][0][tid] = R.F0;
       fsm[0][1][tid] = R.F1;
-      if (knot_row && node == 0 && A.k_max > 0)
-        *reinterpret_cast<double4*>(knot_row) = make_double4(t0, y00, y01, R.F1);
+      if (A.knots && node == 0 && A.k_max > 0)
+        *reinterpret_cast<double4*>(A.knots + (size_t)prob * A.k_max * FX_KNOT) = make_double4(t0, y00, y01, R.F1);
       n_knots = 1;
       double h0, d1;
       init_h0(y00, y01, R.F0, R.F1, tol, h0, d1);
@@ -384,9 +424,9 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
         y01 = s.y11;
         fsm[0][0][tid] = f0;  // FSAL
         fsm[0][1][tid] = f1;
-        if (knot_row && node == 0 && n_knots < A.k_max) {
-          double4* dst = reinterpret_cast<double4*>(knot_row + (size_t)n_knots * FX_KNOT);
-          *dst = make_double4(t0, y00, y01, f1);
+        if (A.knots && node == 0 && n_knots < A.k_max) {
+          double* knot_row = A.knots + (size_t)prob * A.k_max * FX_KNOT;
+          *reinterpret_cast<double4*>(knot_row + (size_t)n_knots * FX_KNOT) = make_double4(t0, y00, y01, f1);
         }
         n_knots++;
         if (event_fired(direction, y00, y01, bnd_i, A.itol)) {
@@ -493,7 +533,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
           __stcg(s2 + 3, make_double2(bis.lower, bis.upper));
           __stcg(C, make_int4(result, n_shots, bis.n_exp, n_att));
           __stcg(C + 1, make_int4(n_rej, n_rhs, n_att, e.knots));
-          atomicAdd((unsigned long long*)&ctl->remaining, (unsigned long long)(-1LL));
+          atomicAdd((unsigned long long*)&ctx.ctl->remaining, (unsigned long long)(-1LL));
         } else {
           // not converged: save the bisection state and queue the problem's next shot(s)
           __stcg(S + 6, bis.lower);
@@ -506,9 +546,9 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
           // choice a pure function of (problem, shot, problems remaining).
           int d = 1;
           if (can_speculate && bis.phase == 2) {
-            long long rem = *(volatile long long*)&ctl->remaining;
+            long long rem = *(volatile long long*)&ctx.ctl->remaining;
             if (rem < 1) rem = 1;
-            const long long rho = n_lanes * 256 / rem;  // lanes per unfinished problem, in 1/256
+            const long long rho = ctx.n_lanes * 256 / rem;  // lanes per unfinished problem, in 1/256
             while (d < SPEC_MAX_DEPTH && ((2LL << d) - 1) * 256 <= rho) d++;
             if (d < SPEC_MAX_DEPTH) {
               const long long lo = ((1LL << d) - 1) * 256, hi = ((2LL << d) - 1) * 256;
@@ -527,8 +567,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
             __stcg(&hdr->k, make_int4((1 << d) - 1, d, 0, 0));
           }
           __threadfence();
-          if (d > 1) push_tasks(ctl, ring, n_work, ring_cap, prob, 1, (1 << d) - 1);
-          else push_tasks(ctl, ring, n_work, ring_cap, prob, 0, 1);
+          if (d > 1) push_tasks(ctx.ctl, ctx.ring, ctx.n_work, ctx.ring_cap, prob, 1, (1 << d) - 1);
+          else push_tasks(ctx.ctl, ctx.ring, ctx.n_work, ctx.ring_cap, prob, 0, 1);
         }
       }
       mode = M_FETCH;

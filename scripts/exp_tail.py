@@ -9,6 +9,9 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import bench  # noqa: E402
 from frontx_b200 import _lib  # noqa: E402
 
+import os
+if os.environ.get("FX_LIB"):
+    _lib.LIB_PATH = Path(os.environ["FX_LIB"]).resolve()
 L = _lib.lib()
 dev = torch.device("cuda", 0)
 N = 100_000
