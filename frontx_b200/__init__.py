@@ -8,7 +8,8 @@ compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
 """
 
 from . import D, models
-from ._forward import RESULTS, BatchSolution, Solution, SolveError, solve, solve_batch, solve_batch_host
+from ._forward import (RESULTS, BatchSolution, Solution, SolveError, solve, solve_batch, solve_batch_host,
+                       solve_flowrate, solve_flowrate_batch)
 from ._inverse import BatchInverse, InterpolatedSolution, inverse, sorptivity
 from ._lib import FrontxB200Error
 from .models import ModelBatch
@@ -30,5 +31,7 @@ __all__ = [
     "solve",
     "solve_batch",
     "solve_batch_host",
+    "solve_flowrate",
+    "solve_flowrate_batch",
     "sorptivity",
 ]

@@ -62,6 +62,7 @@ class BatchSolution:
         self.knots = knots
         self.k_max = int(k_max)
         self.itol = float(itol)
+        self.b = None  # boundary values found by solve_flowrate_batch (None for solve_batch: b is an input)
 
     def __len__(self) -> int:
         return int(self.summary.shape[0])
@@ -169,6 +170,7 @@ class BatchSolution:
             j += len(self)
         sub = BatchSolution(self.models[j], self.summary[j:j + 1], self.counters[j:j + 1],
                             None if self.knots is None else self.knots[j:j + 1], self.k_max, self.itol)
+        sub.b = None if self.b is None else self.b[j:j + 1]
         return Solution(sub)
 
     def cpu(self) -> dict:
@@ -225,6 +227,8 @@ class Solution(AbstractSolution):
 
     @property
     def b(self) -> float:  # _forward.py:49-52
+        if getattr(self._batch, "b", None) is not None:  # flow-rate boundary: b is a result
+            return float(self._batch.b[0].item())
         return float(self._batch.knots[0, 0, 1].item()) if self._batch.knots is not None else float("nan")
 
     @property
@@ -321,6 +325,120 @@ def solve(  # noqa: PLR0913
     return sol
 
 
+_RADIAL_K = {"cylindrical": 1, "polar": 1, "spherical": 2}
+
+
+def _flux_density(Qb: Any, radial: str, ob: float, angle: float | None, height: float | None) -> tuple[np.ndarray, int]:
+    """Inlet flux density q with d_dob = -q/D(b) (fronts.solve_flowrate)."""
+    if radial not in _RADIAL_K:
+        raise ValueError(f"radial must be one of {sorted(_RADIAL_K)}, got {radial!r}")
+    Qb = np.asarray(Qb, dtype=np.float64)
+    if radial == "cylindrical":
+        if height is None:
+            raise TypeError("cylindrical flow needs a height")
+        area = (2 * np.pi if angle is None else angle) * ob * height
+    elif radial == "polar":
+        if height is not None:
+            raise TypeError("polar flow takes no height")
+        area = (2 * np.pi if angle is None else angle) * ob
+    else:
+        if height is not None:
+            raise TypeError("spherical flow takes no height")
+        area = (4 * np.pi if angle is None else angle) * ob * ob
+    return Qb / area, _RADIAL_K[radial]
+
+
+def solve_flowrate_batch(  # noqa: PLR0913
+    D: Any,
+    *,
+    Qb: Any,
+    i: Any,
+    radial: str = "cylindrical",
+    ob: float = 1e-6,
+    angle: float | None = None,
+    height: float | None = None,
+    itol: float = 1e-3,
+    max_steps: int = 100,
+    throw: bool = True,
+    k_max: int = 256,
+    b_bracket: Any = None,
+    device: Any = None,
+    options: dict | None = None,
+) -> BatchSolution:
+    """Radial problems with a FLOW-RATE boundary, n at a time (north-star config C4).
+
+    Not in the reference; semantics are those of ``fronts.solve_flowrate``:
+    the ODE gains the radial term ``k/o`` (k = 1 cylindrical/polar, 2 spherical), the boundary sits
+    at ``ob > 0``, the inlet value ``b`` is unknown and the inlet gradient follows from the imposed
+    flow rate, ``d_dob = -Qb / (D(b) * angle * ob * height)``.  The shooting bisection runs on ``b``
+    inside ``b_bracket`` (default: from ``i`` to just below the model's saturated value; models with
+    no upper bound need an explicit bracket) until the far field meets ``i`` within ``itol``.
+    The returned ``BatchSolution`` has the usual layout; ``.b`` holds the boundary values found.
+    """
+    models = _as_batch(D)
+    torch = _lib.require_cuda()
+    n = len(models)
+    q, radial_k = _flux_density(Qb, radial, ob, angle, height)
+    i_np = np.broadcast_to(np.asarray(i, dtype=np.float64), (n,)).copy()
+    if b_bracket is None:
+        hi = models.saturation()
+        if not np.all(np.isfinite(hi)):
+            raise ValueError("models without a saturated value need an explicit b_bracket=(lo, hi)")
+        lo_np, hi_np = i_np.copy(), hi
+    else:
+        lo_np = np.broadcast_to(np.asarray(b_bracket[0], dtype=np.float64), (n,)).copy()
+        hi_np = np.broadcast_to(np.asarray(b_bracket[1], dtype=np.float64), (n,)).copy()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ids, par = models.to_device(dev)
+    q_t = torch.as_tensor(np.broadcast_to(q, (n,)).copy(), device=dev)
+    i_t = torch.as_tensor(i_np, device=dev)
+    lo_t = torch.as_tensor(lo_np, device=dev)
+    hi_t = torch.as_tensor(hi_np, device=dev)
+    summary = torch.empty((n, _lib.NSUM), dtype=torch.float64, device=dev)
+    counters = torch.zeros((n, _lib.NCNT), dtype=torch.int32, device=dev)
+    knots = torch.zeros((n, k_max, _lib.KNOT), dtype=torch.float64, device=dev) if k_max > 0 else None
+    opt = _lib.default_options(itol=float(itol), max_bisect=int(max_steps), radial_k=radial_k, ob=float(ob),
+                               **(options or {}))
+    with torch.cuda.device(dev):
+        rc = _lib.lib().fx_solve_flowrate_batch(n, ids.data_ptr(), par.data_ptr(), q_t.data_ptr(), i_t.data_ptr(),
+                                                lo_t.data_ptr(), hi_t.data_ptr(), opt, summary.data_ptr(),
+                                                counters.data_ptr(), k_max,
+                                                knots.data_ptr() if knots is not None else None,
+                                                torch.cuda.current_stream(dev).cuda_stream)
+    _lib.check(rc)
+    # C ABI layout {b, oi, theta(oi), d_dob, D(b), residual, b_lower, b_upper} -> the usual one
+    b_found = summary[:, 0].clone()
+    d_dob = summary[:, 3].clone()
+    summary[:, _lib.S_D_DOB] = d_dob
+    summary[:, _lib.S_S0] = -2.0 * summary[:, _lib.S_D_B] * d_dob
+    sol = BatchSolution(models, summary, counters, knots, k_max, itol)
+    sol.b = b_found
+    sol.ob = float(ob)
+    if throw:
+        sol.raise_for_status()
+    return sol
+
+
+def solve_flowrate(D: Any, *, Qb: float, i: float, radial: str = "cylindrical", ob: float = 1e-6,  # noqa: PLR0913
+                   angle: float | None = None, height: float | None = None, itol: float = 1e-3,
+                   max_steps: int = 100, throw: bool = True, b_bracket: Any = None) -> Solution:
+    """One radial problem with a flow-rate boundary (``fronts.solve_flowrate`` semantics), on the GPU."""
+    k_max = 512
+    while True:
+        batch = solve_flowrate_batch(D, Qb=Qb, i=i, radial=radial, ob=ob, angle=angle, height=height, itol=itol,
+                                     max_steps=max_steps, throw=False, k_max=k_max, b_bracket=b_bracket)
+        if len(batch) != 1:
+            raise ValueError("solve_flowrate() takes one model; use solve_flowrate_batch() for several")
+        nk = int(batch.counters[0, _lib.C_KNOTS].item())
+        if nk <= k_max:
+            break
+        k_max = 1 << (nk - 1).bit_length()
+    sol = Solution(batch)
+    if throw and sol.result != RESULTS.successful:
+        raise SolveError("the shooting bisection on b did not converge (max_steps_reached or no bracket)")
+    return sol
+
+
 def solve_batch_host(models: ModelBatch, b: np.ndarray, i: np.ndarray, *, itol: float = 1e-3,
                      max_steps: int = 100, k_max: int = 0, summary: np.ndarray | None = None,
                      counters: np.ndarray | None = None, options: dict | None = None):
@@ -344,4 +462,4 @@ def solve_batch_host(models: ModelBatch, b: np.ndarray, i: np.ndarray, *, itol: 
 
 
 __all__: Sequence[str] = ("RESULTS", "Solution", "BatchSolution", "SolveError", "solve", "solve_batch",
-                          "solve_batch_host")
+                          "solve_batch_host", "solve_flowrate", "solve_flowrate_batch")

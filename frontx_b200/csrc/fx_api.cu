@@ -43,6 +43,14 @@ int device_info(DeviceInfo* out) {
   if (dev < 0 || dev >= 64) return fail(FX_ERR_CUDA, "device index out of range%s");
   if (!cache[dev].ok) {
     FX_CUDA(cudaDeviceGetAttribute(&cache[dev].sms, cudaDevAttrMultiProcessorCount, dev));
+    // the per-call scratch comes from the stream-ordered pool: keep freed blocks cached across
+    // synchronisations instead of returning them to the driver after every call
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
     cache[dev].ok = true;
   }
   *out = cache[dev];
@@ -91,45 +99,50 @@ __global__ void scatter_models_kernel(long long n, const int* __restrict__ model
   }
 }
 
-template <int MODEL>
-int launch_model(const fx::SolveArgs& a, bool radial, int grid, cudaStream_t s) {
-  if (radial)
-    fx::shoot_bisect_kernel<MODEL, true><<<grid, fx::SOLVE_BLOCK, 0, s>>>(a);
-  else
-    fx::shoot_bisect_kernel<MODEL, false><<<grid, fx::SOLVE_BLOCK, 0, s>>>(a);
+template <int MODEL, int GEOM>
+int launch_geom(const fx::SolveArgs& a, int grid, cudaStream_t s) {
+  fx::shoot_bisect_kernel<MODEL, GEOM><<<grid, fx::SOLVE_BLOCK, 0, s>>>(a);
   g_launches++;
   FX_CUDA(cudaGetLastError());
   return FX_OK;
 }
 
+// geom: 0 planar, 1 radial, 2 radial with a flow-rate boundary (template parameter GEOM)
 template <int MODEL>
-int occupancy_of(bool radial, int* blocks) {
+int launch_model(const fx::SolveArgs& a, int geom, int grid, cudaStream_t s) {
+  if (geom == 2) return launch_geom<MODEL, 2>(a, grid, s);
+  if (geom == 1) return launch_geom<MODEL, 1>(a, grid, s);
+  return launch_geom<MODEL, 0>(a, grid, s);
+}
+
+template <int MODEL, int GEOM>
+int occupancy_geom(int* blocks) {
   // the kernel keeps its per-lane state in shared memory: ask for the largest carve-out
-  if (radial) {
-    FX_CUDA(cudaFuncSetAttribute(fx::shoot_bisect_kernel<MODEL, true>,
-                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        blocks, fx::shoot_bisect_kernel<MODEL, true>, fx::SOLVE_BLOCK, 0));
-  } else {
-    FX_CUDA(cudaFuncSetAttribute(fx::shoot_bisect_kernel<MODEL, false>,
-                                 cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        blocks, fx::shoot_bisect_kernel<MODEL, false>, fx::SOLVE_BLOCK, 0));
-  }
+  FX_CUDA(cudaFuncSetAttribute(fx::shoot_bisect_kernel<MODEL, GEOM>,
+                               cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  FX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, fx::shoot_bisect_kernel<MODEL, GEOM>,
+                                                        fx::SOLVE_BLOCK, 0));
   return FX_OK;
 }
 
-int launch_by_id(int model, const fx::SolveArgs& a, bool radial, long long n_upper, int sms,
+template <int MODEL>
+int occupancy_of(int geom, int* blocks) {
+  if (geom == 2) return occupancy_geom<MODEL, 2>(blocks);
+  if (geom == 1) return occupancy_geom<MODEL, 1>(blocks);
+  return occupancy_geom<MODEL, 0>(blocks);
+}
+
+int launch_by_id(int model, const fx::SolveArgs& a, int geom, long long n_upper, int sms,
                  cudaStream_t s) {
   int bps = 1, rc = FX_OK;
   switch (model) {
-    case FX_CONSTANT: rc = occupancy_of<FX_CONSTANT>(radial, &bps); break;
-    case FX_POWER_LAW: rc = occupancy_of<FX_POWER_LAW>(radial, &bps); break;
-    case FX_BROOKS_COREY: rc = occupancy_of<FX_BROOKS_COREY>(radial, &bps); break;
-    case FX_VAN_GENUCHTEN: rc = occupancy_of<FX_VAN_GENUCHTEN>(radial, &bps); break;
-    case FX_LETXS: rc = occupancy_of<FX_LETXS>(radial, &bps); break;
-    case FX_LETD: rc = occupancy_of<FX_LETD>(radial, &bps); break;
-    case FX_LOG: rc = occupancy_of<FX_LOG>(radial, &bps); break;
+    case FX_CONSTANT: rc = occupancy_of<FX_CONSTANT>(geom, &bps); break;
+    case FX_POWER_LAW: rc = occupancy_of<FX_POWER_LAW>(geom, &bps); break;
+    case FX_BROOKS_COREY: rc = occupancy_of<FX_BROOKS_COREY>(geom, &bps); break;
+    case FX_VAN_GENUCHTEN: rc = occupancy_of<FX_VAN_GENUCHTEN>(geom, &bps); break;
+    case FX_LETXS: rc = occupancy_of<FX_LETXS>(geom, &bps); break;
+    case FX_LETD: rc = occupancy_of<FX_LETD>(geom, &bps); break;
+    case FX_LOG: rc = occupancy_of<FX_LOG>(geom, &bps); break;
     default: return fail(FX_ERR_MODEL, "unknown model id%s");
   }
   if (rc) return rc;
@@ -141,13 +154,13 @@ int launch_by_id(int model, const fx::SolveArgs& a, bool radial, long long n_upp
   int grid = (int)(even < cap ? even : cap);
   if (grid < 1) grid = 1;
   switch (model) {
-    case FX_CONSTANT: return launch_model<FX_CONSTANT>(a, radial, grid, s);
-    case FX_POWER_LAW: return launch_model<FX_POWER_LAW>(a, radial, grid, s);
-    case FX_BROOKS_COREY: return launch_model<FX_BROOKS_COREY>(a, radial, grid, s);
-    case FX_VAN_GENUCHTEN: return launch_model<FX_VAN_GENUCHTEN>(a, radial, grid, s);
-    case FX_LETXS: return launch_model<FX_LETXS>(a, radial, grid, s);
-    case FX_LETD: return launch_model<FX_LETD>(a, radial, grid, s);
-    default: return launch_model<FX_LOG>(a, radial, grid, s);
+    case FX_CONSTANT: return launch_model<FX_CONSTANT>(a, geom, grid, s);
+    case FX_POWER_LAW: return launch_model<FX_POWER_LAW>(a, geom, grid, s);
+    case FX_BROOKS_COREY: return launch_model<FX_BROOKS_COREY>(a, geom, grid, s);
+    case FX_VAN_GENUCHTEN: return launch_model<FX_VAN_GENUCHTEN>(a, geom, grid, s);
+    case FX_LETXS: return launch_model<FX_LETXS>(a, geom, grid, s);
+    case FX_LETD: return launch_model<FX_LETD>(a, geom, grid, s);
+    default: return launch_model<FX_LOG>(a, geom, grid, s);
   }
 }
 
@@ -297,6 +310,42 @@ __global__ void dfma_peak_kernel(double* sink, int iters, double seed) {
   if (s == 123.456) sink[0] = s;
 }
 
+// flow-rate boundary: fills summary[3] = d_dob = -q/D(b) and summary[4] = D(b) at the accepted b
+template <int MODEL>
+__device__ void flow_finalize_one(const double* p, double q, double* S) {
+  double d[fx::NDERIVED];
+  fx::derive_params<MODEL>(p, d, fx::g_math_tab_dev);
+  double D, D1, D2, iD;
+  fx::eval_D<MODEL>(d, S[0], false, D, D1, D2, iD, fx::g_math_tab_dev);
+  S[3] = -q * iD;
+  S[4] = D;
+}
+
+__global__ void flow_finalize_kernel(long long n, const int* __restrict__ model_id,
+                                     const double* __restrict__ params, const double* __restrict__ q,
+                                     double* summary, const int* __restrict__ counters) {
+  for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
+       j += (long long)gridDim.x * blockDim.x) {
+    if (counters[j * FX_NCNT] < 0) continue;  // invalid model id: never solved
+    const double* p = params + j * FX_NPARAM;
+    double* S = summary + j * FX_NSUM;
+    switch (model_id[j]) {
+      case FX_CONSTANT: flow_finalize_one<FX_CONSTANT>(p, q[j], S); break;
+      case FX_POWER_LAW: flow_finalize_one<FX_POWER_LAW>(p, q[j], S); break;
+      case FX_BROOKS_COREY: flow_finalize_one<FX_BROOKS_COREY>(p, q[j], S); break;
+      case FX_VAN_GENUCHTEN: flow_finalize_one<FX_VAN_GENUCHTEN>(p, q[j], S); break;
+      case FX_LETXS: flow_finalize_one<FX_LETXS>(p, q[j], S); break;
+      case FX_LETD: flow_finalize_one<FX_LETD>(p, q[j], S); break;
+      case FX_LOG: flow_finalize_one<FX_LOG>(p, q[j], S); break;
+      default: break;
+    }
+  }
+}
+
+int solve_impl(int64_t n, const int32_t* model_id, const double* params, const double* b,
+               const double* i, const double* q, const double* b_hi, const fx_solve_options* opt_in,
+               double* summary, int32_t* counters, int32_t k_max, double* knots, void* stream);
+
 int grid_for(long long total, int block, int sms) {
   long long want = (total + block - 1) / block;
   long long cap = (long long)sms * 16;
@@ -349,6 +398,28 @@ int fx_device_count(void) {
 int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, const double* b,
                    const double* i, const fx_solve_options* opt_in, double* summary,
                    int32_t* counters, int32_t k_max, double* knots, void* stream) {
+  return solve_impl(n, model_id, params, b, i, nullptr, nullptr, opt_in, summary, counters, k_max, knots, stream);
+}
+
+int fx_solve_flowrate_batch(int64_t n, const int32_t* model_id, const double* params, const double* q,
+                            const double* i, const double* b_lo, const double* b_hi,
+                            const fx_solve_options* opt_in, double* summary, int32_t* counters,
+                            int32_t k_max, double* knots, void* stream) {
+  if (n > 0 && (!q || !b_lo || !b_hi)) return fail(FX_ERR_ARG, "null pointer argument%s");
+  fx_solve_options o;
+  if (opt_in) o = *opt_in; else { fx_default_solve_options(&o); o.radial_k = 1; o.ob = 1e-6; }
+  if (o.radial_k < 1) return fail(FX_ERR_ARG, "a flow-rate boundary needs radial_k = 1 or 2 and ob > 0%s");
+  o.max_expansions = 0;  // the bracket on b is the caller's; it is not widened
+  return solve_impl(n, model_id, params, b_lo, i, q, b_hi, &o, summary, counters, k_max, knots, stream);
+}
+
+}  // extern "C"
+
+namespace {
+
+int solve_impl(int64_t n, const int32_t* model_id, const double* params, const double* b,
+               const double* i, const double* q, const double* b_hi, const fx_solve_options* opt_in,
+               double* summary, int32_t* counters, int32_t k_max, double* knots, void* stream) {
   if (n < 0 || k_max < 0) return fail(FX_ERR_ARG, "negative size%s");
   if (n == 0) return FX_OK;
   if (!model_id || !params || !b || !i || !summary || !counters)
@@ -405,6 +476,8 @@ int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, con
   a.params = params;
   a.b = b;
   a.i = i;
+  a.q = q;
+  a.b_hi = b_hi;
   a.summary = summary;
   a.counters = counters;
   a.knots = k_max > 0 ? knots : nullptr;
@@ -432,11 +505,17 @@ int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, con
     a.slot = m;
     const bool timing = g_kernel_timing.load() != 0;
     if (timing) FX_CUDA(cudaEventRecord(fk->k0[m], fk->streams[m]));
-    if ((rc = launch_by_id(m, a, o.radial_k > 0, n, di.sms, fk->streams[m]))) return rc;
+    if ((rc = launch_by_id(m, a, q ? 2 : (o.radial_k > 0 ? 1 : 0), n, di.sms, fk->streams[m]))) return rc;
     if (timing) FX_CUDA(cudaEventRecord(fk->k1[m], fk->streams[m]));
     fk->timed[m] = timing;
     FX_CUDA(cudaEventRecord(fk->done[m], fk->streams[m]));
     FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
+  }
+  if (q) {
+    // flow-rate boundary: d_dob = -q/D(b) and D(b) at the accepted b, by the same evaluation the shots used
+    flow_finalize_kernel<<<grid_for(n, 256, di.sms), 256, 0, s>>>(n, model_id, params, q, summary, counters);
+    g_launches++;
+    FX_CUDA(cudaGetLastError());
   }
   if (spec) FX_CUDA(cudaFreeAsync(spec, s));
   FX_CUDA(cudaFreeAsync(bstate, s));
@@ -446,6 +525,10 @@ int fx_solve_batch(int64_t n, const int32_t* model_id, const double* params, con
   FX_CUDA(cudaFreeAsync(scratch, s));
   return FX_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 int fx_solve_batch_host(int64_t n, const int32_t* model_id, const double* params, const double* b,
                         const double* i, const fx_solve_options* opt, double* summary,

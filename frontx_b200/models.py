@@ -254,6 +254,17 @@ class ModelBatch:
         ids = np.atleast_1d(self.model_id[idx])
         return ModelBatch(ids, self.params[idx].reshape(ids.size, _lib.NPARAM))
 
+    def saturation(self, margin: float = 1e-7) -> np.ndarray:
+        """Largest boundary value worth bracketing per problem: ``theta_s - margin*(theta_s - theta_r)``
+        for the models with a saturated value, ``inf`` for the unbounded closed forms."""
+        col = {_lib.BROOKS_COREY: (4, 5), _lib.VAN_GENUCHTEN: (5, 6), _lib.LETXS: (8, 9), _lib.LETD: (4, 5)}
+        out = np.full(len(self), np.inf)
+        for mid, (r, s_) in col.items():
+            sel = self.model_id == mid
+            tr, ts = self.params[sel, r], self.params[sel, s_]
+            out[sel] = ts - margin * (ts - tr)
+        return out
+
     def to_device(self, device=None):
         torch = _lib.require_cuda()
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

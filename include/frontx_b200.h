@@ -18,8 +18,8 @@
  *   - plain pointers and sizes only; no torch / CUDA-runtime types in signatures
  *     (`stream` is a cudaStream_t passed as void*; NULL = legacy default stream);
  *   - `*_batch` entry points take DEVICE pointers owned by the caller and are
- *     asynchronous on `stream`; nothing allocated by a call outlives it except
- *     a small per-device work-queue counter block cached by the library;
+ *     asynchronous on `stream`; scratch (queue, per-problem bisection state) is taken
+ *     from and returned to the stream-ordered memory pool inside the call;
  *   - `*_host` entry points take HOST pointers, stage through device memory the
  *     library owns, and return after the results are back in host memory;
  *   - return 0 on success, negative on error; fx_last_error() gives the text
@@ -98,8 +98,10 @@ void fx_default_solve_options(fx_solve_options *opt);
 
 /* Replaces frontx.solve (src/frontx/_forward.py:60-122) for a batch of n
  * independent problems: Kvaerno5 ESDIRK shots (diffrax, :84-95) with the boolean
- * event (:76-78), bisection on d_dob (:104-112).  One GPU thread owns one
- * problem.  k_max = 0 skips dense output; otherwise knots is [n][k_max][4] and
+ * event (:76-78), bisection on d_dob (:104-112).  Persistent lanes pop single
+ * shots from a device-wide queue (fx_solve.cuh); with k_max = 0 idle lanes also run
+ * the next levels of a problem's bisection tree speculatively (same results).
+ * k_max = 0 skips dense output; otherwise knots is [n][k_max][4] and
  * rows hold the last shot's accepted steps (n_knots may exceed k_max: the table
  * is then truncated and Solution evaluation refuses it).  All pointers device. */
 int fx_solve_batch(int64_t n, const int32_t *model_id, const double *params /*[n][12]*/,
@@ -112,6 +114,22 @@ int fx_solve_batch(int64_t n, const int32_t *model_id, const double *params /*[n
 int fx_solve_batch_host(int64_t n, const int32_t *model_id, const double *params,
                         const double *b, const double *i, const fx_solve_options *opt,
                         double *summary, int32_t *counters, int32_t k_max, double *knots);
+
+/* Radial problems with a FLOW-RATE boundary (north-star config C4).  Not in the reference:
+ * semantics of fronts.solve_flowrate on the reference's algorithm.
+ * The ODE has the radial term k/o (opt->radial_k = 1 cylindrical/polar, 2 spherical), the
+ * boundary is at opt->ob > 0, the inlet value b is unknown and every shot starts from
+ * (b, d_dob = -q/D(b)) with q[j] = Qb/(angle*ob*height) the imposed inlet flux density.  The
+ * bisection of src/frontx/_forward.py:104-112 runs on b inside [b_lo, b_hi] (not widened:
+ * FX_NO_BRACKET if the residuals at both ends have one sign) until |theta(oi) - i| < itol.
+ *   summary[j] = {b, oi, theta(oi), d_dob = -q/D(b), D(b), residual, b_lower, b_upper}
+ * counters, k_max and knots as in fx_solve_batch.  All pointers device. */
+int fx_solve_flowrate_batch(int64_t n, const int32_t *model_id, const double *params /*[n][12]*/,
+                            const double *q /*[n]*/, const double *i /*[n]*/,
+                            const double *b_lo /*[n]*/, const double *b_hi /*[n]*/,
+                            const fx_solve_options *opt /*host; NULL = defaults, cylindrical, ob=1e-6*/,
+                            double *summary /*[n][8]*/, int32_t *counters /*[n][8]*/,
+                            int32_t k_max, double *knots /*[n][k_max][4] or NULL*/, void *stream);
 
 /* Replaces Solution.__call__ / Solution.d_do (src/frontx/_forward.py:25-37):
  * clip o to [0, oi], locate the step, cubic Hermite dense output.  o_query is

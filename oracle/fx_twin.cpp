@@ -181,6 +181,70 @@ int solve_one(const double* p, double b, double i, const Options& o, double* sum
   return result;
 }
 
+// Flow-rate boundary (north-star C4; fronts.solve_flowrate semantics): the
+// inlet value b is unknown, the inlet flux density q = Qb/(angle ob height) is given, so every
+// shot starts from (b, d_dob = -q/D(b)) and the bisection runs on b inside [b_lo, b_hi].
+template <int MODEL>
+int solve_one_flow(const double* p, double q, double i, double b_lo, double b_hi, const Options& o,
+                   double* summary, int32_t* counters, int k_max, double* knots) {
+  using namespace fx;
+  double dpar[NDERIVED];
+  derive_params<MODEL>(p, dpar, MT);
+  Bisect bis;
+  bis.lower = b_lo;
+  bis.upper = b_hi;
+  bis.phase = 0;
+  bis.lo_neg = 0;
+  bis.n_bis = 0;
+  bis.n_exp = 0;
+  bis.d_cur = b_lo;
+  Counters c;
+  int result;
+  Shot last;
+  double b_shot, D_b = 0.0, d_dob = 0.0;
+  do {
+    b_shot = bis.d_cur;
+    double D, D1, D2, iD;
+    eval_D<MODEL>(dpar, b_shot, false, D, D1, D2, iD, MT);
+    D_b = D;
+    d_dob = -q * iD;
+    last = shoot<MODEL>(dpar, b_shot, i, d_dob, o, c, k_max, knots);
+    c.n_shots++;
+    result = bis.next(last.residual, o.itol, o.max_bisect, 0);
+  } while (result < 0);
+  summary[0] = b_shot;
+  summary[1] = last.t_end;
+  summary[2] = last.theta_end;
+  summary[3] = d_dob;
+  summary[4] = D_b;
+  summary[5] = last.residual;
+  summary[6] = bis.lower;
+  summary[7] = bis.upper;
+  counters[0] = result;
+  counters[1] = c.n_shots;
+  counters[2] = bis.n_exp;
+  counters[3] = c.n_att;
+  counters[4] = c.n_rej;
+  counters[5] = c.n_rhs;
+  counters[6] = c.n_jac;
+  counters[7] = c.n_knots;
+  return result;
+}
+
+int flow_dispatch(int model, const double* p, double q, double i, double b_lo, double b_hi, const Options& o,
+                  double* summary, int32_t* counters, int k_max, double* knots) {
+  switch (model) {
+    case FX_CONSTANT: return solve_one_flow<FX_CONSTANT>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    case FX_POWER_LAW: return solve_one_flow<FX_POWER_LAW>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    case FX_BROOKS_COREY: return solve_one_flow<FX_BROOKS_COREY>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    case FX_VAN_GENUCHTEN: return solve_one_flow<FX_VAN_GENUCHTEN>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    case FX_LETXS: return solve_one_flow<FX_LETXS>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    case FX_LETD: return solve_one_flow<FX_LETD>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    case FX_LOG: return solve_one_flow<FX_LOG>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    default: counters[0] = -1; return -1;
+  }
+}
+
 int solve_dispatch(int model, const double* p, double b, double i, const Options& o, double* summary,
                    int32_t* counters, int k_max, double* knots) {
   switch (model) {
@@ -207,6 +271,7 @@ struct Batch {
   int64_t n;
   const int32_t* model;
   const double *params, *b, *i;
+  const double *q = nullptr, *b_hi = nullptr;  // flow-rate boundary: flux density and upper bracket (b is the lower)
   Options o;
   double* summary;
   int32_t* counters;
@@ -221,10 +286,15 @@ void* worker(void* arg) {
     long long j0 = B->next.fetch_add(4);
     if (j0 >= B->n) break;
     long long j1 = j0 + 4 < B->n ? j0 + 4 : B->n;
-    for (long long j = j0; j < j1; j++)
-      solve_dispatch(B->model[j], B->params + (size_t)FX_NPARAM * j, B->b[j], B->i[j], B->o,
-                     B->summary + (size_t)FX_NSUM * j, B->counters + (size_t)FX_NCNT * j, B->k_max,
-                     B->knots ? B->knots + (size_t)FX_KNOT * B->k_max * j : nullptr);
+    for (long long j = j0; j < j1; j++) {
+      double* kn = B->knots ? B->knots + (size_t)FX_KNOT * B->k_max * j : nullptr;
+      if (B->q)
+        flow_dispatch(B->model[j], B->params + (size_t)FX_NPARAM * j, B->q[j], B->i[j], B->b[j], B->b_hi[j], B->o,
+                      B->summary + (size_t)FX_NSUM * j, B->counters + (size_t)FX_NCNT * j, B->k_max, kn);
+      else
+        solve_dispatch(B->model[j], B->params + (size_t)FX_NPARAM * j, B->b[j], B->i[j], B->o,
+                       B->summary + (size_t)FX_NSUM * j, B->counters + (size_t)FX_NCNT * j, B->k_max, kn);
+    }
   }
   return nullptr;
 }
@@ -250,6 +320,11 @@ double fxt_log(double x) { return fx::fx_log(x, MT); }
 double fxt_exp(double x) { return fx::fx_exp(x, MT); }
 double fxt_expm1(double x) { return fx::fx_expm1(x, MT); }
 
+int fxt_solve_flowrate_batch(int64_t n, const int32_t* model, const double* params, const double* q,
+                             const double* i, const double* b_lo, const double* b_hi, double itol,
+                             int max_bisect, int max_ode_steps, double rtol, double atol, int radial_k, double ob,
+                             double* summary, int32_t* counters, int k_max, double* knots, int nthreads);
+
 int fxt_solve_batch(int64_t n, const int32_t* model, const double* params, const double* b, const double* i,
                     double itol, int max_bisect, int max_ode_steps, double rtol, double atol,
                     int max_expansions, int radial_k, double ob, double* summary, int32_t* counters,
@@ -261,6 +336,37 @@ int fxt_solve_batch(int64_t n, const int32_t* model, const double* params, const
   B.b = b;
   B.i = i;
   B.o = Options{itol, rtol, atol, ob, max_bisect, max_ode_steps, max_expansions, radial_k};
+  B.summary = summary;
+  B.counters = counters;
+  B.k_max = k_max;
+  B.knots = knots;
+  if (nthreads <= 0) {
+    long c = sysconf(_SC_NPROCESSORS_ONLN);
+    nthreads = c > 0 ? (int)c : 1;
+  }
+  if (nthreads > 256) nthreads = 256;
+  pthread_t th[256];
+  int started = 0;
+  for (int t = 1; t < nthreads; t++)
+    if (pthread_create(&th[started], nullptr, worker, &B) == 0) started++;
+  worker(&B);
+  for (int t = 0; t < started; t++) pthread_join(th[t], nullptr);
+  return 0;
+}
+
+int fxt_solve_flowrate_batch(int64_t n, const int32_t* model, const double* params, const double* q,
+                             const double* i, const double* b_lo, const double* b_hi, double itol,
+                             int max_bisect, int max_ode_steps, double rtol, double atol, int radial_k, double ob,
+                             double* summary, int32_t* counters, int k_max, double* knots, int nthreads) {
+  Batch B;
+  B.n = n;
+  B.model = model;
+  B.params = params;
+  B.b = b_lo;
+  B.i = i;
+  B.q = q;
+  B.b_hi = b_hi;
+  B.o = Options{itol, rtol, atol, ob, max_bisect, max_ode_steps, 0, radial_k};
   B.summary = summary;
   B.counters = counters;
   B.k_max = k_max;

@@ -75,6 +75,10 @@ def twin() -> C.CDLL:
         L.fxt_solve_batch.argtypes = [C.c_int64, ip, dp, dp, dp, C.c_double, C.c_int, C.c_int, C.c_double,
                                       C.c_double, C.c_int, C.c_int, C.c_double, dp, ip, C.c_int, dp, C.c_int]
         L.fxt_solve_batch.restype = C.c_int
+        L.fxt_solve_flowrate_batch.argtypes = [C.c_int64, ip, dp, dp, dp, dp, dp, C.c_double, C.c_int, C.c_int,
+                                               C.c_double, C.c_double, C.c_int, C.c_double, dp, ip, C.c_int, dp,
+                                               C.c_int]
+        L.fxt_solve_flowrate_batch.restype = C.c_int
         _twin = L
     return _twin
 
@@ -106,6 +110,25 @@ def twin_solve_batch(model, params, b, i, itol: float = 1e-3, max_steps: int = 1
                            int(max_ode_steps), float(rtol), float(atol), int(max_expansions), int(radial_k),
                            float(ob), _dp(summary), _ip(counters), k_max,
                            _dp(knots) if knots is not None else None, int(nthreads))
+    return {"summary": summary, "counters": counters, "knots": knots}
+
+
+def twin_solve_flowrate_batch(model, params, q, i, b_lo, b_hi, itol: float = 1e-3, max_steps: int = 100,
+                              k_max: int = 0, nthreads: int = 0, max_ode_steps: int = 4096, rtol: float = 1e-3,
+                              atol: float = 1e-6, radial_k: int = 1, ob: float = 1e-6):
+    """Flow-rate boundary (bisection on b): summary = {b, oi, theta(oi), d_dob, D(b), residual, b_lower, b_upper}."""
+    model = np.ascontiguousarray(model, dtype=np.int32)
+    n = model.size
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(n, NPARAM)
+    full = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,)))  # noqa: E731
+    q, i, b_lo, b_hi = full(q), full(i), full(b_lo), full(b_hi)
+    summary = np.empty((n, NSUM))
+    counters = np.zeros((n, NCNT), dtype=np.int32)
+    knots = np.zeros((n, k_max, 4)) if k_max > 0 else None
+    twin().fxt_solve_flowrate_batch(n, _ip(model), _dp(params), _dp(q), _dp(i), _dp(b_lo), _dp(b_hi), float(itol),
+                                    int(max_steps), int(max_ode_steps), float(rtol), float(atol), int(radial_k),
+                                    float(ob), _dp(summary), _ip(counters), k_max,
+                                    _dp(knots) if knots is not None else None, int(nthreads))
     return {"summary": summary, "counters": counters, "knots": knots}
 
 
