@@ -6,7 +6,8 @@ BASELINE config C2, the 10^5-problem van Genuchten (alpha, n, Ks) sweep for
 horizontal imbibition (b = 0.7 - 1e-7, i = 0.025, itol = 1e-3), per GPU.  With
 N GPUs every rank solves its own 10^5-problem sweep (weak scaling, no data-path
 collective) and the 64-byte result records are all-gathered over NCCL inside
-the timed region.
+the timed region.  The kernel is the persistent shot-queue kernel of
+frontx_b200/csrc/fx_solve.cuh (one launch per step does the whole sweep).
 
     python bench.py --gpus 1 --steps 5 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -119,6 +120,21 @@ class ClockSampler:
                 "sm_max_mhz": float(max(smax)) if smax else None,
                 "power_w_max": float(max(power)) if power else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def ncu_dram_bytes_per_launch(n: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/, taken at 10^5 problems per launch); None for other sizes."""
+    path = ROOT / "profiles" / "r1_vg_kernel_ncu_raw_n100k.txt"
+    if n != 100_000 or not path.exists():
+        return None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for line in path.read_text().splitlines():
+        f = line.split()
+        if len(f) == 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[1] in unit:
+            total += float(f[2]) * unit[f[1]]
+    return total or None
 
 
 def cpu_arm(models, n_sample: int, threads: int):
@@ -273,7 +289,7 @@ def run_ours(args) -> None:
     roofline = {
         "bound": "fp64", "kernel": "fx::shoot_bisect_kernel<van_genuchten>",
         "achieved": achieved / 1e12, "peak": peak.value / 1e12, "unit": "TFLOP/s",
-        "frac": achieved / peak.value, "traffic": None,
+        "frac": achieved / peak.value, "traffic": ncu_dram_bytes_per_launch(n),
         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
         "algorithmic_flops_per_solve": flops / n,
         "hbm_gbs": n * (BYTES_IN + BYTES_OUT) / (k_ms * 1e-3) / 1e9,
