@@ -63,6 +63,24 @@ def test_diffusivity_vs_oracle_dense(fxo, paper):
         np.testing.assert_allclose(m.derivatives(th), fxo.D(m.model_id, m.params(), th), rtol=1e-13, atol=1e-300)
 
 
+def test_reciprocal_and_elementary_functions_bitwise_vs_twin(fxo):
+    """fx_rcp on the device is the hardware seed + two Newton steps with select-handled edges, on the
+    host the IEEE division under the same definition (fx_math.cuh): the two must agree bit for bit,
+    edges included.  D' of the log model is c1*D*rcp(theta*D) and D of the power law is
+    exp(k*log(theta)), so equality of the model derivatives over many theta -- ordinary, tiny, huge,
+    zero, negative -- pins the reciprocal, log and exp of the device to the twin's."""
+    rng = np.random.default_rng(7)
+    th = np.concatenate([np.exp(rng.uniform(-30, 3, 20000)), np.exp(rng.uniform(-740, 700, 4000)),
+                         [0.0, -0.0, 5e-324, 1e-310, 2.2250738585072014e-308, 1e-301, 1e-300, 1e300, 1e301,
+                          1.7976931348623157e308, np.inf, -1.0, -np.inf, np.nan]])
+    for m in (fx.D.philip_exact(), fx.D.power_law(k=2.5, a=3.0, epsilon=0.1), fx.D.power_law(k=4)):
+        got = m.derivatives(th)
+        want = fxo.twin_D(m.model_id, m.params(), th)
+        fin = ~np.isnan(want)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), type(m).__name__  # NaN where the twin has NaN
+        assert np.array_equal(got[fin].view(np.int64), want[fin].view(np.int64)), type(m).__name__
+
+
 def test_diffusivity_outside_domain_is_nan(paper):
     m = paper["VG(n)"]
     out = m.derivatives(np.array([m.theta_range[0] - 1e-3, m.theta_range[1] + 1e-3]))
