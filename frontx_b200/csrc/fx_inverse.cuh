@@ -26,11 +26,21 @@
 //   earlier tile is resident or finished: no deadlock, no serial chain, and the
 //   result is bit-reproducible run to run)
 //   D = -d * (prefix + local)/2, written coalesced in the caller's point order.
+//
+// Arithmetic: an fp64 division costs ~25 issue slots on sm_100a (scripts/ubench_fp64.cu), and
+// scipy's formulas written literally take 12 per point, which made the first version of this
+// kernel issue-bound at 13 % of the HBM roofline.  Here every interval's two secants
+// (do/dtheta and dtheta/do, reciprocals of one another) are formed once, by the branch-free
+// reciprocal of fx_math.cuh, and shared with the neighbouring point through a warp shuffle; the
+// harmonic mean of the interior slope, 1/((w1/m0 + w2/m1)/(w1+w2)), becomes
+// (w1+w2)/(w1*im0 + w2*im1) with im the other direction's secant: 4 reciprocals per point.
 #pragma once
 
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+
+#include "fx_math.cuh"
 
 namespace fx {
 
@@ -39,6 +49,7 @@ constexpr int INV_ITEMS = 4;
 constexpr int INV_TILE = INV_BLOCK * INV_ITEMS;
 constexpr int INV_HALO_L = 2;
 constexpr int INV_NAGG = 4;  // inverse integral, forward PCHIP integral, trapezoid, flagged-bad count
+constexpr int INV_GROUP = 32; // tiles per look-back group (one warp reads a group)
 
 struct InvArgs {
   long long batch, npts, ntiles;      // tiles per profile
@@ -49,7 +60,11 @@ struct InvArgs {
   int* status;                        // [batch]
   double* slope;                      // [batch][npts] do/dtheta at the knots, or nullptr
   double* anti;                       // [batch][npts] Int_i^theta o dtheta at the knots, or nullptr
-  double* agg;                        // [batch][ntiles][INV_NAGG]
+  double* agg;                        // [batch][ntiles][INV_NAGG] tile aggregates
+  double* gtot;                       // [batch][ngroups][INV_NAGG] totals of the full groups of INV_GROUP tiles
+  int* gcount;                        // [batch][ngroups] tiles of the group that have published
+  int* gflag;                         // [batch][ngroups] group total published
+  long long ngroups;                  // ceil(ntiles / INV_GROUP)
   int* flag;                          // [batch][ntiles]
   unsigned long long* ticket;
 };
@@ -73,24 +88,28 @@ __device__ __forceinline__ double pchip_edge(double h0, double h1, double m0, do
   return d;
 }
 
-// slope of the PCHIP interpolant y(x) at smem position q (points q-2..q+2 may be read);
-// r is the traversal index of q, n the number of points
-__device__ __forceinline__ double pchip_slope_at(const double* x, const double* y, int q, long long r,
-                                                 long long n) {
-  if (n == 2) {
-    int a = (r == 0) ? q : q - 1;
-    return (y[a + 1] - y[a]) / (x[a + 1] - x[a]);
-  }
-  if (r == 0) {
-    double h0 = x[q + 1] - x[q], h1 = x[q + 2] - x[q + 1];
-    return pchip_edge(h0, h1, (y[q + 1] - y[q]) / h0, (y[q + 2] - y[q + 1]) / h1);
-  }
-  if (r == n - 1) {
-    double h0 = x[q] - x[q - 1], h1 = x[q - 1] - x[q - 2];
-    return pchip_edge(h0, h1, (y[q] - y[q - 1]) / h0, (y[q - 1] - y[q - 2]) / h1);
-  }
-  double h0 = x[q] - x[q - 1], h1 = x[q + 1] - x[q];
-  return pchip_interior(h0, h1, (y[q] - y[q - 1]) / h0, (y[q + 1] - y[q]) / h1);
+// 1/x by the hardware seed and two Newton steps (correctly rounded for ordinary arguments; a
+// zero or non-finite step only occurs in a profile that is flagged non-monotone anyway)
+__device__ __forceinline__ double rcp_lean(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  e = fma(e, e, e);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
+// interior slope from the two secants m0, m1 and their reciprocals im0, im1 (the secants of the
+// inverse function): scipy's weighted harmonic mean with one reciprocal; zero unless the secants
+// have the same strict sign
+__device__ __forceinline__ double pchip_interior_r(double h0, double h1, double m0, double m1, double im0,
+                                                   double im1) {
+  double w1 = fma(2.0, h1, h0);
+  double w2 = fma(2.0, h0, h1);
+  double v = (w1 + w2) * rcp_lean(fma(w1, im0, w2 * im1));
+  bool same = ((m0 > 0.0) && (m1 > 0.0)) || ((m0 < 0.0) && (m1 < 0.0));
+  return same ? v : 0.0;
 }
 
 __device__ __forceinline__ double warp_incl_scan(double v, unsigned lane) {
@@ -107,12 +126,14 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(INV_BLOCK) inverse_scan_kernel(const InvArgs A) {
+__global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArgs A) {
   constexpr int NS = INV_TILE + INV_HALO_L + 2;  // points held: halo 2 left, 2 right (1 used + pad)
   __shared__ double s_th[NS], s_o[NS];
-  __shared__ double s_d[INV_TILE + 1], s_df[INV_TILE + 1];  // slopes do/dtheta and dtheta/do
-  __shared__ double s_warp[3][INV_BLOCK / 32];
-  __shared__ double s_gather[INV_NAGG][INV_BLOCK / 32];
+  __shared__ double s_d[2][INV_TILE + 1];  // do/dtheta at the tile's points; two buffers: a tile's
+                                           // output is written one tile later (see below)
+  __shared__ double s_df[INV_TILE + 1];    // dtheta/do
+  __shared__ double s_warp[2][INV_BLOCK / 32];
+  __shared__ double s_scan[INV_ITEMS][INV_BLOCK / 32];
   __shared__ double s_red[INV_NAGG];
   __shared__ unsigned long long s_ticket;
   __shared__ int s_bad;
@@ -120,6 +141,17 @@ __global__ void __launch_bounds__(INV_BLOCK) inverse_scan_kernel(const InvArgs A
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
   const long long total_tiles = A.batch * A.ntiles;
+  const long long n = A.npts;
+  const bool two = (n == 2);
+
+  // The prefix of a tile needs the aggregates of every earlier tile of its profile, which other
+  // CTAs are computing at the same moment: waiting for them right away left 45 % of the warp
+  // time at that barrier.  So a tile publishes its aggregate, the CTA goes on to load and scan
+  // its NEXT tile, and only then resolves the previous tile's prefix and writes its output.
+  // Aggregates are published before anything is waited for, so this cannot deadlock.
+  long long pv_p = -1, pv_t = 0;  // the deferred tile
+  double pv_excl[INV_ITEMS] = {0.0, 0.0, 0.0, 0.0};
+  int pv_buf = 0, buf = 0;
 
   for (;;) {
     __syncthreads();
@@ -129,175 +161,265 @@ __global__ void __launch_bounds__(INV_BLOCK) inverse_scan_kernel(const InvArgs A
     }
     __syncthreads();
     const long long ticket = (long long)s_ticket;
-    if (ticket >= total_tiles) break;
-    const long long p = ticket / A.ntiles, t = ticket - p * A.ntiles;
-    const long long n = A.npts;
-    const long long r0 = t * INV_TILE;
-    const double* th_g = A.theta + p * n;
-    const double* o_g = A.o + p * n;
+    const bool have = ticket < total_tiles;
+    if (!have && pv_p < 0) break;
+    long long p = 0, t = 0;
+    double excl[INV_ITEMS] = {0.0, 0.0, 0.0, 0.0};
 
-    // ---- load tile + halo in traversal order (r -> caller index n-1-r) ----
-    for (int q = tid; q < NS; q += INV_BLOCK) {
-      long long r = r0 - INV_HALO_L + q;
-      double a = 0.0, b = 0.0;
-      if (r >= 0 && r < n) {
-        long long j = n - 1 - r;
-        a = th_g[j];
-        b = o_g[j];
-      }
-      s_th[q] = a;
-      s_o[q] = b;
-    }
-    __syncthreads();
+    if (have) {
+      p = ticket / A.ntiles;
+      t = ticket - p * A.ntiles;
+      const long long r0 = t * INV_TILE;
+      const double* th_g = A.theta + p * n;
+      const double* o_g = A.o + p * n;
+      double* sd = s_d[buf];
+      const double dir_step = th_g[n - 2] - th_g[n - 1];  // issued early: needed after the slopes
 
-    // ---- slopes for r in [r0, r0+TILE] ------------------------------------
-    for (int e = tid; e <= INV_TILE; e += INV_BLOCK) {
-      long long r = r0 + e;
-      double d = 0.0, df = 0.0;
-      if (r < n) {
-        int q = e + INV_HALO_L;
-        d = pchip_slope_at(s_th, s_o, q, r, n);   // do/dtheta   (inverse interpolant)
-        df = pchip_slope_at(s_o, s_th, q, r, n);  // dtheta/do   (forward interpolant)
-      }
-      s_d[e] = d;
-      s_df[e] = df;
-    }
-    __syncthreads();
-
-    // ---- per-interval integrals and the block scan ---------------------------
-    double excl[INV_ITEMS];
-    double carry = 0.0, sumF = 0.0, sumT = 0.0;
-    int bad = 0;
-    const double sign_ref = sgn(th_g[n - 2] - th_g[n - 1]);  // profile direction, from interval r=0
-#pragma unroll
-    for (int it = 0; it < INV_ITEMS; it++) {
-      int e = it * INV_BLOCK + tid;
-      long long r = r0 + e;
-      double I = 0.0;
-      if (r < n - 1) {
-        int q = e + INV_HALO_L;
-        double hx = s_th[q + 1] - s_th[q];  // signed step in theta
-        double ho = s_o[q + 1] - s_o[q];    // signed step in o
-        if (!(sgn(hx) == sign_ref) || sign_ref == 0.0) bad = 1;
-        I = hx * (s_o[q] + s_o[q + 1]) * 0.5 + hx * hx * (s_d[e] - s_d[e + 1]) * (1.0 / 12.0);
-        sumF += ho * (s_th[q] + s_th[q + 1]) * 0.5 + ho * ho * (s_df[e] - s_df[e + 1]) * (1.0 / 12.0);
-        sumT += ho * (s_th[q] + s_th[q + 1]) * 0.5;
-      }
-      double inc = warp_incl_scan(I, lane);
-      if (lane == 31) s_warp[0][wid] = inc;
-      __syncthreads();
-      double woff = 0.0, wtot = 0.0;
-#pragma unroll
-      for (int w = 0; w < INV_BLOCK / 32; w++) {
-        double v = s_warp[0][w];
-        if (w < (int)wid) woff += v;
-        wtot += v;
-      }
-      double up = __shfl_up_sync(0xffffffffu, inc, 1);
-      excl[it] = carry + woff + (lane ? up : 0.0);
-      carry += wtot;
-      __syncthreads();
-    }
-    // reductions of the two sorptivity integrands (fixed tree)
-    sumF = warp_sum(sumF);
-    sumT = warp_sum(sumT);
-    if (lane == 0) {
-      s_warp[1][wid] = sumF;
-      s_warp[2][wid] = sumT;
-    }
-    if (bad) atomicOr(&s_bad, 1);
-    __syncthreads();
-    if (tid == 0) {
-      double f = 0.0, z = 0.0;
-      for (int w = 0; w < INV_BLOCK / 32; w++) {
-        f += s_warp[1][w];
-        z += s_warp[2][w];
-      }
-      double* ag = A.agg + (p * A.ntiles + t) * INV_NAGG;
-      ag[0] = carry;
-      ag[1] = f;
-      ag[2] = z;
-      ag[3] = (double)s_bad;
-      __threadfence();
-      atomicExch(A.flag + p * A.ntiles + t, 1);
-    }
-
-    // ---- prefix over earlier tiles of this profile, fixed summation order -----
-    double part[INV_NAGG] = {0.0, 0.0, 0.0, 0.0};
-    const bool last_tile = (t == A.ntiles - 1);
-    for (long long k = tid; k < t; k += INV_BLOCK) {
-      volatile int* fl = A.flag + p * A.ntiles + k;
-      while (*fl == 0) __nanosleep(40);
-      __threadfence();
-      const double* ag = A.agg + (p * A.ntiles + k) * INV_NAGG;
-      part[0] += __ldcg(ag + 0);
-      if (last_tile) {
-        part[1] += __ldcg(ag + 1);
-        part[2] += __ldcg(ag + 2);
-        part[3] += __ldcg(ag + 3);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < INV_NAGG; c++) {
-      double v = warp_sum(part[c]);
-      if (lane == 0) s_gather[c][wid] = v;
-    }
-    __syncthreads();
-    if (tid < INV_NAGG) {
-      double acc = 0.0;
-      for (int w = 0; w < INV_BLOCK / 32; w++) acc += s_gather[tid][w];
-      s_red[tid] = acc;
-    }
-    __syncthreads();
-    const double prefix = s_red[0];
-
-    // ---- D at the tile's points, caller order --------------------------------
-#pragma unroll
-    for (int it = 0; it < INV_ITEMS; it++) {
-      int e = it * INV_BLOCK + tid;
-      long long r = r0 + e;
-      if (r < n) {
-        double Iod = prefix + excl[it];
-        long long j = p * n + (n - 1 - r);
-        A.D[j] = -(s_d[e] * Iod) * 0.5;
-        if (A.slope) A.slope[j] = s_d[e];
-        if (A.anti) A.anti[j] = Iod;
-      }
-    }
-
-    // ---- the last tile of a profile closes its sorptivity sums and status ------
-    if (last_tile && tid == 0) {
-      const double* own = A.agg + (p * A.ntiles + t) * INV_NAGG;
-      double F = s_red[1] + own[1], Z = s_red[2] + own[2], nbad = s_red[3] + own[3];
-      // traversal runs from o_last down to o_first: Int_{o_first}^{o_last} theta do = -sum
-      double* out = A.sorp + p * 4;
-      out[0] = -F;
-      out[1] = -Z;
-      // extrapolation of the first forward cubic from o_first back to 0 (scipy extrapolate=True)
-      double ext = 0.0;
-      double o0 = o_g[0];
-      if (o0 != 0.0 && n >= 2) {
-        double o1 = o_g[1], y0 = th_g[0], y1 = th_g[1];
-        double hh = o1 - o0, m = (y1 - y0) / hh;
-        double d0, d1;
-        if (n == 2) {
-          d0 = d1 = m;
-        } else {
-          double o2 = o_g[2], y2 = th_g[2];
-          double h1 = o2 - o1, m1 = (y2 - y1) / h1;
-          d0 = pchip_edge(hh, h1, m, m1);
-          d1 = (n == 3) ? pchip_edge(h1, hh, m1, m) : pchip_interior(hh, h1, m, m1);
+      // ---- load tile + halo in traversal order (r -> caller index n-1-r) ----
+      for (int q = tid; q < NS; q += INV_BLOCK) {
+        long long r = r0 - INV_HALO_L + q;
+        double a = 0.0, b = 0.0;
+        if (r >= 0 && r < n) {
+          long long j = n - 1 - r;
+          a = th_g[j];
+          b = o_g[j];
         }
-        double tt = (d0 + d1 - 2.0 * m) / hh;
-        double c0 = tt / hh, c1 = (m - d0) / hh - tt, c2 = d0, c3 = y0;
-        double u = 0.0 - o0;  // antiderivative at o=0 relative to o0
-        double anti = (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + c2 * 0.5) * u + c3) * u;
-        ext = -anti;  // Int_0^{o0}
+        s_th[q] = a;
+        s_o[q] = b;
       }
-      out[2] = ext;
-      out[3] = 0.0;
-      A.status[p] = (nbad != 0.0) ? 1 : 0;
+      __syncthreads();
+
+      // ---- slopes do/dtheta (inverse interpolant) and dtheta/do (forward) at r in [r0, r0+TILE] --
+      // Each lane forms the secants of the interval to the RIGHT of its point; the interval to the
+      // left is the previous lane's (one shuffle; lane 0 of a warp recomputes it).
+      for (int e = tid; e < INV_TILE + INV_BLOCK; e += INV_BLOCK) {
+        const long long r = r0 + e;
+        const int q = e + INV_HALO_L;
+        const bool live = (e <= INV_TILE) && (r < n);
+        double hx1 = 0.0, ho1 = 0.0, m1 = 0.0, mf1 = 0.0;  // interval (q, q+1)
+        if (live && r < n - 1) {
+          hx1 = s_th[q + 1] - s_th[q];
+          ho1 = s_o[q + 1] - s_o[q];
+          m1 = ho1 * rcp_lean(hx1);
+          mf1 = hx1 * rcp_lean(ho1);
+        }
+        double hx0 = __shfl_up_sync(0xffffffffu, hx1, 1), ho0 = __shfl_up_sync(0xffffffffu, ho1, 1);
+        double m0 = __shfl_up_sync(0xffffffffu, m1, 1), mf0 = __shfl_up_sync(0xffffffffu, mf1, 1);
+        if (lane == 0 && live && r >= 1) {  // interval (q-1, q)
+          hx0 = s_th[q] - s_th[q - 1];
+          ho0 = s_o[q] - s_o[q - 1];
+          m0 = ho0 * rcp_lean(hx0);
+          mf0 = hx0 * rcp_lean(ho0);
+        }
+        if (live) {
+          double d, df;
+          if (two) {
+            d = (r == 0) ? m1 : m0;
+            df = (r == 0) ? mf1 : mf0;
+          } else if (r == 0) {  // one-sided: intervals (q, q+1) and (q+1, q+2)
+            double hx2 = s_th[q + 2] - s_th[q + 1], ho2 = s_o[q + 2] - s_o[q + 1];
+            d = pchip_edge(hx1, hx2, m1, ho2 / hx2);
+            df = pchip_edge(ho1, ho2, mf1, hx2 / ho2);
+          } else if (r == n - 1) {  // one-sided, mirrored: intervals (q-1, q) and (q-2, q-1)
+            double hxm = s_th[q - 1] - s_th[q - 2], hom = s_o[q - 1] - s_o[q - 2];
+            d = pchip_edge(hx0, hxm, m0, hom / hxm);
+            df = pchip_edge(ho0, hom, mf0, hxm / hom);
+          } else {
+            d = pchip_interior_r(hx0, hx1, m0, m1, mf0, mf1);
+            df = pchip_interior_r(ho0, ho1, mf0, mf1, m0, m1);
+          }
+          sd[e] = d;
+          s_df[e] = df;
+        } else if (e <= INV_TILE) {
+          sd[e] = 0.0;
+          s_df[e] = 0.0;
+        }
+      }
+      __syncthreads();
+
+      // ---- per-interval integrals and the block scan (one barrier) -----------------
+      double incl[INV_ITEMS], mine[INV_ITEMS];
+      double sumF = 0.0, sumT = 0.0;
+      int bad = 0;
+      const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);  // profile direction, from interval r=0
+#pragma unroll
+      for (int it = 0; it < INV_ITEMS; it++) {
+        int e = it * INV_BLOCK + tid;
+        long long r = r0 + e;
+        double I = 0.0;
+        if (r < n - 1) {
+          int q = e + INV_HALO_L;
+          double hx = s_th[q + 1] - s_th[q];  // signed step in theta
+          double ho = s_o[q + 1] - s_o[q];    // signed step in o
+          if (flat || !(up ? hx > 0.0 : hx < 0.0)) bad = 1;
+          double trap = ho * (s_th[q] + s_th[q + 1]) * 0.5;
+          I = hx * (s_o[q] + s_o[q + 1]) * 0.5 + hx * hx * (sd[e] - sd[e + 1]) * (1.0 / 12.0);
+          sumF += trap + ho * ho * (s_df[e] - s_df[e + 1]) * (1.0 / 12.0);
+          sumT += trap;
+        }
+        mine[it] = I;
+        incl[it] = warp_incl_scan(I, lane);
+        if (lane == 31) s_scan[it][wid] = incl[it];
+      }
+      sumF = warp_sum(sumF);  // the two sorptivity integrands (fixed tree)
+      sumT = warp_sum(sumT);
+      if (lane == 0) {
+        s_warp[0][wid] = sumF;
+        s_warp[1][wid] = sumT;
+      }
+      if (bad) atomicOr(&s_bad, 1);
+      __syncthreads();
+      double carry = 0.0;
+#pragma unroll
+      for (int it = 0; it < INV_ITEMS; it++) {
+        double woff = 0.0, wtot = 0.0;
+#pragma unroll
+        for (int w = 0; w < INV_BLOCK / 32; w++) {
+          double v = s_scan[it][w];
+          if (w < (int)wid) woff += v;
+          wtot += v;
+        }
+        excl[it] = carry + woff + (incl[it] - mine[it]);
+        carry += wtot;
+      }
+
+      // ---- publish the tile aggregate; close the group if this is its last tile to arrive ------
+      if (wid == 0) {
+        if (lane == 0) {
+          double f = 0.0, z = 0.0;
+          for (int w = 0; w < INV_BLOCK / 32; w++) {
+            f += s_warp[0][w];
+            z += s_warp[1][w];
+          }
+          double* ag = A.agg + (p * A.ntiles + t) * INV_NAGG;
+          __stcg(ag + 0, carry);
+          __stcg(ag + 1, f);
+          __stcg(ag + 2, z);
+          __stcg(ag + 3, (double)s_bad);
+          __threadfence();
+          atomicExch(A.flag + p * A.ntiles + t, 1);
+        }
+        const long long g = t / INV_GROUP, g0 = g * INV_GROUP;
+        const bool full = g < A.ntiles / INV_GROUP;
+        int arrived = 0;
+        if (lane == 0 && full) arrived = atomicAdd(A.gcount + p * A.ngroups + g, 1);
+        arrived = __shfl_sync(0xffffffffu, arrived, 0);
+        if (full && arrived == INV_GROUP - 1) {
+          __threadfence();
+          const double* ag = A.agg + (p * A.ntiles + g0 + lane) * INV_NAGG;
+          double tot[INV_NAGG];
+#pragma unroll
+          for (int c = 0; c < INV_NAGG; c++) tot[c] = warp_sum(__ldcg(ag + c));
+          if (lane == 0) {
+            double* gt = A.gtot + (p * A.ngroups + g) * INV_NAGG;
+#pragma unroll
+            for (int c = 0; c < INV_NAGG; c++) __stcg(gt + c, tot[c]);
+            __threadfence();
+            atomicExch(A.gflag + p * A.ngroups + g, 1);
+          }
+        }
+      }
+    }
+
+    // ---- the deferred tile: prefix over the earlier tiles of its profile, then its output --------
+    // Two fixed levels, no chain: whoever publishes the last aggregate of a group of INV_GROUP
+    // tiles also publishes the group total (above); a tile adds the totals of all earlier groups
+    // and the aggregates of its own group's earlier tiles.  O(ntiles/INV_GROUP + INV_GROUP) reads
+    // and -- the association being fixed by the tile index alone -- bit-reproducible run to run.
+    if (pv_p >= 0) {
+      const long long p2 = pv_p, t2 = pv_t;
+      if (wid == 0) {
+        const long long g = t2 / INV_GROUP, g0 = g * INV_GROUP;
+        double part[INV_NAGG] = {0.0, 0.0, 0.0, 0.0};
+        for (long long gi = lane; gi < g; gi += 32) {
+          volatile int* fl = A.gflag + p2 * A.ngroups + gi;
+          while (*fl == 0) __nanosleep(32);
+          __threadfence();
+          const double* gt = A.gtot + (p2 * A.ngroups + gi) * INV_NAGG;
+#pragma unroll
+          for (int c = 0; c < INV_NAGG; c++) part[c] += __ldcg(gt + c);
+        }
+        const long long k = g0 + lane;
+        if (k < t2) {
+          volatile int* fl = A.flag + p2 * A.ntiles + k;
+          while (*fl == 0) __nanosleep(32);
+          __threadfence();
+          const double* ag = A.agg + (p2 * A.ntiles + k) * INV_NAGG;
+#pragma unroll
+          for (int c = 0; c < INV_NAGG; c++) part[c] += __ldcg(ag + c);
+        }
+#pragma unroll
+        for (int c = 0; c < INV_NAGG; c++) part[c] = warp_sum(part[c]);
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < INV_NAGG; c++) s_red[c] = part[c];
+        }
+      }
+      __syncthreads();
+      const double prefix = s_red[0];
+      const long long r0 = t2 * INV_TILE;
+      const double* sd = s_d[pv_buf];
+
+      // D at the tile's points, caller order
+#pragma unroll
+      for (int it = 0; it < INV_ITEMS; it++) {
+        int e = it * INV_BLOCK + tid;
+        long long r = r0 + e;
+        if (r < n) {
+          double Iod = prefix + pv_excl[it];
+          long long j = p2 * n + (n - 1 - r);
+          A.D[j] = -(sd[e] * Iod) * 0.5;
+          if (A.slope) A.slope[j] = sd[e];
+          if (A.anti) A.anti[j] = Iod;
+        }
+      }
+
+      // the last tile of a profile closes its sorptivity sums and status
+      if (t2 == A.ntiles - 1 && tid == 0) {
+        const double* th_g = A.theta + p2 * n;
+        const double* o_g = A.o + p2 * n;
+        const double* own = A.agg + (p2 * A.ntiles + t2) * INV_NAGG;
+        double F = s_red[1] + __ldcg(own + 1), Z = s_red[2] + __ldcg(own + 2), nbad = s_red[3] + __ldcg(own + 3);
+        // traversal runs from o_last down to o_first: Int_{o_first}^{o_last} theta do = -sum
+        double* out = A.sorp + p2 * 4;
+        out[0] = -F;
+        out[1] = -Z;
+        // extrapolation of the first forward cubic from o_first back to 0 (scipy extrapolate=True)
+        double ext = 0.0;
+        double o0 = o_g[0];
+        if (o0 != 0.0 && n >= 2) {
+          double o1 = o_g[1], y0 = th_g[0], y1 = th_g[1];
+          double hh = o1 - o0, m = (y1 - y0) / hh;
+          double d0, d1;
+          if (n == 2) {
+            d0 = d1 = m;
+          } else {
+            double o2 = o_g[2], y2 = th_g[2];
+            double h1 = o2 - o1, m1 = (y2 - y1) / h1;
+            d0 = pchip_edge(hh, h1, m, m1);
+            d1 = (n == 3) ? pchip_edge(h1, hh, m1, m) : pchip_interior(hh, h1, m, m1);
+          }
+          double tt = (d0 + d1 - 2.0 * m) / hh;
+          double c0 = tt / hh, c1 = (m - d0) / hh - tt, c2 = d0, c3 = y0;
+          double u = 0.0 - o0;  // antiderivative at o=0 relative to o0
+          double anti = (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + c2 * 0.5) * u + c3) * u;
+          ext = -anti;  // Int_0^{o0}
+        }
+        out[2] = ext;
+        out[3] = 0.0;
+        A.status[p2] = (nbad != 0.0) ? 1 : 0;
+      }
+    }
+
+    if (have) {
+      pv_p = p;
+      pv_t = t;
+#pragma unroll
+      for (int it = 0; it < INV_ITEMS; it++) pv_excl[it] = excl[it];
+      pv_buf = buf;
+      buf ^= 1;
+    } else {
+      pv_p = -1;
     }
   }
 }
@@ -409,14 +531,19 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   a.slope = slope;
   a.anti = anti;
   size_t tiles = (size_t)batch * (size_t)a.ntiles;
-  size_t agg_bytes = tiles * INV_NAGG * sizeof(double);
-  size_t flag_bytes = tiles * sizeof(int);
+  a.ngroups = (a.ntiles + INV_GROUP - 1) / INV_GROUP;
+  size_t groups = (size_t)batch * (size_t)a.ngroups;
+  size_t agg_bytes = (tiles + groups) * INV_NAGG * sizeof(double);  // tile aggregates, then group totals
+  size_t flag_bytes = ((tiles + 2 * groups) * sizeof(int) + 7) / 8 * 8;  // flag, gcount, gflag
   char* scratch = nullptr;
   cudaError_t e = cudaMallocAsync((void**)&scratch, agg_bytes + flag_bytes + 64, s);
   if (e != cudaSuccess) return e;
   a.agg = reinterpret_cast<double*>(scratch);
+  a.gtot = a.agg + tiles * INV_NAGG;
   a.flag = reinterpret_cast<int*>(scratch + agg_bytes);
-  a.ticket = reinterpret_cast<unsigned long long*>(scratch + agg_bytes + ((flag_bytes + 7) / 8) * 8);
+  a.gcount = a.flag + tiles;
+  a.gflag = a.gcount + groups;
+  a.ticket = reinterpret_cast<unsigned long long*>(scratch + agg_bytes + flag_bytes);
   e = cudaMemsetAsync(scratch + agg_bytes, 0, flag_bytes + 64, s);
   if (e != cudaSuccess) return e;
   int bps = 1;
