@@ -63,9 +63,7 @@ struct InvArgs {
   double* agg;                        // [batch][ntiles][INV_NAGG] tile aggregates
   double* gtot;                       // [batch][ngroups][INV_NAGG] totals of the full groups of INV_GROUP tiles
   int* gcount;                        // [batch][ngroups] tiles of the group that have published
-  int* gflag;                         // [batch][ngroups] group total published
   long long ngroups;                  // ceil(ntiles / INV_GROUP)
-  int* flag;                          // [batch][ntiles]
   unsigned long long* ticket;
 };
 
@@ -124,6 +122,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
   return v;
+}
+
+// Aggregates are published without flags: the scratch is preset to an all-ones pattern (a NaN no
+// computation produces) and a reader spins until the words it needs differ from it.  One L2 round
+// trip when the value is there instead of three (flag, fence, data), no fence on the reader's
+// side (each 8-byte access is atomic): the look-back sits on every tile's critical path.
+__device__ __forceinline__ bool is_unset(double v) { return __double_as_longlong(v) == -1LL; }
+__device__ __forceinline__ void wait_load4(const double* src, double (&v)[4]) {
+  for (;;) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) v[c] = __ldcg(src + c);
+    if (!(is_unset(v[0]) || is_unset(v[1]) || is_unset(v[2]) || is_unset(v[3]))) break;
+    __nanosleep(20);
+  }
 }
 
 __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArgs A) {
@@ -296,8 +308,7 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
           __stcg(ag + 1, f);
           __stcg(ag + 2, z);
           __stcg(ag + 3, (double)s_bad);
-          __threadfence();
-          atomicExch(A.flag + p * A.ntiles + t, 1);
+          __threadfence();  // ordered before the arrival count below
         }
         const long long g = t / INV_GROUP, g0 = g * INV_GROUP;
         const bool full = g < A.ntiles / INV_GROUP;
@@ -305,17 +316,14 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
         if (lane == 0 && full) arrived = atomicAdd(A.gcount + p * A.ngroups + g, 1);
         arrived = __shfl_sync(0xffffffffu, arrived, 0);
         if (full && arrived == INV_GROUP - 1) {
-          __threadfence();
-          const double* ag = A.agg + (p * A.ntiles + g0 + lane) * INV_NAGG;
           double tot[INV_NAGG];
+          wait_load4(A.agg + (p * A.ntiles + g0 + lane) * INV_NAGG, tot);
 #pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) tot[c] = warp_sum(__ldcg(ag + c));
+          for (int c = 0; c < INV_NAGG; c++) tot[c] = warp_sum(tot[c]);
           if (lane == 0) {
             double* gt = A.gtot + (p * A.ngroups + g) * INV_NAGG;
 #pragma unroll
             for (int c = 0; c < INV_NAGG; c++) __stcg(gt + c, tot[c]);
-            __threadfence();
-            atomicExch(A.gflag + p * A.ngroups + g, 1);
           }
         }
       }
@@ -332,21 +340,17 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
         const long long g = t2 / INV_GROUP, g0 = g * INV_GROUP;
         double part[INV_NAGG] = {0.0, 0.0, 0.0, 0.0};
         for (long long gi = lane; gi < g; gi += 32) {
-          volatile int* fl = A.gflag + p2 * A.ngroups + gi;
-          while (*fl == 0) __nanosleep(32);
-          __threadfence();
-          const double* gt = A.gtot + (p2 * A.ngroups + gi) * INV_NAGG;
+          double v[INV_NAGG];
+          wait_load4(A.gtot + (p2 * A.ngroups + gi) * INV_NAGG, v);
 #pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) part[c] += __ldcg(gt + c);
+          for (int c = 0; c < INV_NAGG; c++) part[c] += v[c];
         }
         const long long k = g0 + lane;
         if (k < t2) {
-          volatile int* fl = A.flag + p2 * A.ntiles + k;
-          while (*fl == 0) __nanosleep(32);
-          __threadfence();
-          const double* ag = A.agg + (p2 * A.ntiles + k) * INV_NAGG;
+          double v[INV_NAGG];
+          wait_load4(A.agg + (p2 * A.ntiles + k) * INV_NAGG, v);
 #pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) part[c] += __ldcg(ag + c);
+          for (int c = 0; c < INV_NAGG; c++) part[c] += v[c];
         }
 #pragma unroll
         for (int c = 0; c < INV_NAGG; c++) part[c] = warp_sum(part[c]);
@@ -534,17 +538,17 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   a.ngroups = (a.ntiles + INV_GROUP - 1) / INV_GROUP;
   size_t groups = (size_t)batch * (size_t)a.ngroups;
   size_t agg_bytes = (tiles + groups) * INV_NAGG * sizeof(double);  // tile aggregates, then group totals
-  size_t flag_bytes = ((tiles + 2 * groups) * sizeof(int) + 7) / 8 * 8;  // flag, gcount, gflag
+  size_t cnt_bytes = (groups * sizeof(int) + 7) / 8 * 8;            // arrival counts of the groups
   char* scratch = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&scratch, agg_bytes + flag_bytes + 64, s);
+  cudaError_t e = cudaMallocAsync((void**)&scratch, agg_bytes + cnt_bytes + 64, s);
   if (e != cudaSuccess) return e;
   a.agg = reinterpret_cast<double*>(scratch);
   a.gtot = a.agg + tiles * INV_NAGG;
-  a.flag = reinterpret_cast<int*>(scratch + agg_bytes);
-  a.gcount = a.flag + tiles;
-  a.gflag = a.gcount + groups;
-  a.ticket = reinterpret_cast<unsigned long long*>(scratch + agg_bytes + flag_bytes);
-  e = cudaMemsetAsync(scratch + agg_bytes, 0, flag_bytes + 64, s);
+  a.gcount = reinterpret_cast<int*>(scratch + agg_bytes);
+  a.ticket = reinterpret_cast<unsigned long long*>(scratch + agg_bytes + cnt_bytes);
+  e = cudaMemsetAsync(scratch, 0xff, agg_bytes, s);  // the "unset" pattern (see is_unset)
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(scratch + agg_bytes, 0, cnt_bytes + 64, s);
   if (e != cudaSuccess) return e;
   int bps = 1;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, inverse_scan_kernel, INV_BLOCK, 0);

@@ -9,6 +9,9 @@ import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from frontx_b200 import _lib  # noqa: E402
 
+import os
+if os.environ.get("FX_LIB"):
+    _lib.LIB_PATH = Path(os.environ["FX_LIB"]).resolve()
 L = _lib.lib()
 dev = torch.device("cuda", 0)
 stream = torch.cuda.current_stream(dev)
