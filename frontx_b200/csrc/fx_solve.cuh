@@ -56,6 +56,8 @@ constexpr int SOLVE_BLOCK = 128;
 constexpr int SOLVE_CTAS_PER_SM = 5;             // 128 registers per thread: 4 warps per SM sub-partition
 constexpr int SPEC_MAX_DEPTH = 5;                // up to 31 speculative shots per problem
 constexpr int SPEC_NODES = 1 << SPEC_MAX_DEPTH;  // entries per speculation slot (entry 0 = header)
+constexpr int FX_IN_FLIGHT = -3;                 // counters[.][0] while a problem is unfinished: if a launch ever
+                                                 // ended early (ctl->abort), such problems do not read as solved
 
 __constant__ Tableau c_tab = FX_TABLEAU_INIT;
 
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
               __stcg(S + 6, bnd_b);
               __stcg(S + 7, A.b_hi[prob]);
               int4* c = reinterpret_cast<int4*>(A.counters + (size_t)prob * FX_NCNT);
-              __stcg(c, make_int4(0, 0, 0, 0));
+              __stcg(c, make_int4(FX_IN_FLIGHT, 0, 0, 0));
               __stcg(c + 1, make_int4(0, 0, 0, 0));
               __stcg(&A.bstate[prob], make_int2(0, 0));
               d_shot = bnd_b;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       __stcg(S + 6, bis.lower);
       __stcg(S + 7, bis.upper);
       int4* c = reinterpret_cast<int4*>(A.counters + (size_t)prob * FX_NCNT);
-      __stcg(c, make_int4(0, 0, 0, 0));
+      __stcg(c, make_int4(FX_IN_FLIGHT, 0, 0, 0));
       __stcg(c + 1, make_int4(0, 0, 0, 0));
       __stcg(&A.bstate[prob], make_int2(0, 0));
       d_shot = bis.lower;
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
           // not converged: save the bisection state and queue the problem's next shot(s)
           __stcg(S + 6, bis.lower);
           __stcg(S + 7, bis.upper);
-          __stcg(C, make_int4(0, n_shots, bis.n_exp, n_att));
+          __stcg(C, make_int4(FX_IN_FLIGHT, n_shots, bis.n_exp, n_att));
           __stcg(C + 1, make_int4(n_rej, n_rhs, n_att, e.knots));
           // Speculation depth: batches of 2^d - 1 shots, sized so that the batches of all
           // unfinished problems together fill the resident lanes (rho = lanes per problem);

@@ -68,7 +68,9 @@ enum fx_model {
 enum fx_result {
   FX_SUCCESSFUL = 0,
   FX_MAX_STEPS_REACHED = 1, /* bisection used max_bisect steps without |residual| < itol */
-  FX_NO_BRACKET = 2         /* bracket expansion exhausted without a sign change          */
+  FX_NO_BRACKET = 2,        /* bracket expansion exhausted without a sign change          */
+  FX_INVALID_MODEL = -1,    /* model id outside enum fx_model: the problem was not solved  */
+  FX_UNFINISHED = -3        /* only if a launch ended early on an internal queue error     */
 };
 
 enum fx_error {

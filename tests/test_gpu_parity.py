@@ -257,6 +257,20 @@ def test_mixed_sweep_parity(fxo):
 # ---------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------
+def test_speculative_and_sequential_bisection_agree(fxo):
+    """With k_max = 0 idle lanes run the bisection tree speculatively (a few thousand problems on 95 000
+    lanes: depth 5 from the first midpoint); with dense output requested every shot is sequential.
+    Same summaries, same counters (only shots on the taken path are counted), equal to the twin's."""
+    mb = vg_sweep(3000, seed=11)
+    spec = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    seq = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=8, throw=False)
+    np.testing.assert_array_equal(spec.summary.cpu().numpy(), seq.summary.cpu().numpy())
+    np.testing.assert_array_equal(spec.counters.cpu().numpy(), seq.counters.cpu().numpy())
+    tw = fxo.twin_solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER)
+    np.testing.assert_array_equal(spec.summary.cpu().numpy(), tw["summary"])
+    np.testing.assert_array_equal(spec.counters.cpu().numpy(), tw["counters"])
+
+
 def test_empty_and_single():
     empty = fx.solve_batch(fx.ModelBatch(np.zeros(0, np.int32), np.zeros((0, 12))), b=1.0, i=0.1, k_max=4)
     assert len(empty) == 0
