@@ -2,7 +2,8 @@
 
 Drop-in for the hot path of gerlero/frontx: ``solve`` / ``Solution`` (plus the
 batched ``solve_batch``), the tagged diffusivity models, and the profile -> D
-inverse (``InterpolatedSolution``, ``sorptivity``, batched ``inverse``).  All
+inverse (``InterpolatedSolution``, ``sorptivity``, batched ``inverse``), and the
+parametric ``fit`` / ``ScaledSolution`` that call the solve a generation at a time.  All
 compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
 ``include/frontx_b200.h``; there is no CPU fallback.
 """
@@ -10,6 +11,7 @@ compute runs in hand-written sm_100a CUDA kernels behind the C ABI of
 from . import D, models
 from ._forward import (RESULTS, BatchSolution, Solution, SolveError, solve, solve_batch, solve_batch_host,
                        solve_flowrate, solve_flowrate_batch)
+from ._fit import Param, ScaledSolution, fit
 from ._inverse import BatchInverse, InterpolatedSolution, inverse, sorptivity
 from ._lib import FrontxB200Error
 from .models import ModelBatch
@@ -24,8 +26,11 @@ __all__ = [
     "FrontxB200Error",
     "InterpolatedSolution",
     "ModelBatch",
+    "Param",
+    "ScaledSolution",
     "Solution",
     "SolveError",
+    "fit",
     "inverse",
     "models",
     "solve",

@@ -49,6 +49,7 @@ EXPORTS = (
     "fx_solve_batch_host",
     "fx_solve_flowrate_batch",
     "fx_eval_batch",
+    "fx_scaled_fit_batch",
     "fx_diffusivity_batch",
     "fx_inverse_batch",
     "fx_inverse_query_batch",
@@ -82,6 +83,7 @@ def lib() -> C.CDLL:
     L.fx_solve_flowrate_batch.argtypes = [i64, vp, vp, vp, vp, vp, vp, C.POINTER(SolveOptions), vp, vp, i32, vp, vp]
     L.fx_eval_batch.argtypes = [i64, vp, vp, i32, i64, vp, i32, vp, vp, vp]
     L.fx_diffusivity_batch.argtypes = [i64, vp, vp, i64, vp, vp, vp]
+    L.fx_scaled_fit_batch.argtypes = [i64, vp, vp, vp, i32, i64, vp, vp, vp, i32, vp, vp, vp, vp]
     L.fx_inverse_batch.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fx_inverse_query_batch.argtypes = [i64, i64, vp, vp, vp, vp, i64, vp, vp, vp]
     L.fx_pchip_eval_batch.argtypes = [i64, i64, vp, vp, i64, vp, vp, vp]
@@ -92,7 +94,7 @@ def lib() -> C.CDLL:
     L.fx_last_solve_kernel_ms.restype = C.c_int
     L.fx_launch_count.restype = i64
     L.fx_last_error.restype = C.c_char_p
-    for name in ("fx_solve_batch", "fx_solve_batch_host", "fx_solve_flowrate_batch", "fx_eval_batch", "fx_diffusivity_batch",
+    for name in ("fx_solve_batch", "fx_solve_batch_host", "fx_solve_flowrate_batch", "fx_eval_batch", "fx_scaled_fit_batch", "fx_diffusivity_batch",
                  "fx_inverse_batch", "fx_inverse_query_batch", "fx_pchip_eval_batch", "fx_measure_fp64_peak",
                  "fx_version",
                  "fx_device_count"):

@@ -257,6 +257,125 @@ __global__ void eval_kernel(long long n, const int* __restrict__ counters,
   }
 }
 
+// ---- ScaledSolution.fitting_data + the cost of fit(), a batch of candidates at a time -----------
+// (src/frontx/_inverse/fit.py:45-82 and :145-151).  A candidate's solved profile theta(o) is
+// compared with m data points through the one-parameter rescaling o -> o/sqrt(D0); D0 is fitted by
+// damped Gauss-Newton on u = ln D0 (the reference runs optimistix Levenberg-Marquardt on D0 itself,
+// same minimiser), then cost = mean(((theta(o_k/sqrt(D0)) - theta_k) w_k)^2).  One warp per
+// candidate, data points strided over its lanes, fixed shuffle-tree reductions.
+__device__ __forceinline__ void hermite_theta(const double4* K, int nk, double x, double& th, double& dth) {
+  // theta and d theta/dx of the dense-output cubic at x, clipped to the table (jnp.clip, _forward.py:30)
+  const double4 first = K[0], last = K[nk - 1];
+  const bool inside = (x > first.x) && (x < last.x);
+  x = fmin(fmax(x, first.x), last.x);
+  if (nk == 1) {
+    th = first.y;
+    dth = 0.0;
+    return;
+  }
+  int lo = 0, hi = nk;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (K[mid].x < x) lo = mid + 1; else hi = mid;
+  }
+  int idx = min(max(lo - 1, 0), nk - 2);
+  double4 a = K[idx], b = K[idx + 1];
+  double dt = b.x - a.x;
+  double idt = (dt == 0.0) ? 0.0 : 1.0 / dt;
+  double s = (x - a.x) * idt;
+  double k0 = dt * a.z, k1 = dt * b.z;
+  double ca = k0 + k1 + 2.0 * a.y - 2.0 * b.y;
+  double cb = -2.0 * k0 - k1 - 3.0 * a.y + 3.0 * b.y;
+  th = fma(fma(fma(ca, s, cb), s, k0), s, a.y);
+  dth = inside ? fma(fma(3.0 * ca, s, 2.0 * cb), s, k0) * idt : 0.0;
+}
+
+__device__ __forceinline__ double warp_total(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// mode 0: D0 = 1 (cost of the unscaled solution); 1: fit D0 to the data; 2: D0 given in D0_io
+__global__ void scaled_fit_kernel(long long n, const int* __restrict__ counters,
+                                  const double* __restrict__ summary, const double* __restrict__ knots,
+                                  int k_max, int m, const double* __restrict__ o, const double* __restrict__ theta,
+                                  const double* __restrict__ weight, int mode, double* __restrict__ D0_io,
+                                  double* __restrict__ cost, int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  for (long long j = warp; j < n; j += nwarps) {
+    const int nk = counters[j * FX_NCNT + 7];
+    const bool solved = counters[j * FX_NCNT + 0] == 0 && nk >= 1 && nk <= k_max;
+    if (!solved) {  // fit.py:145-151: a failed solve costs inf
+      if (lane == 0) {
+        cost[j] = inf;
+        status[j] = 1;
+        if (mode != 2) D0_io[j] = 1.0;
+      }
+      continue;
+    }
+    const double4* K = reinterpret_cast<const double4*>(knots + (size_t)j * k_max * FX_KNOT);
+    const double oi = summary[j * FX_NSUM + 1];
+    auto sums = [&](double D0, double& c, double& g, double& h) {
+      // c = sum r^2, g = sum r dr/du, h = sum (dr/du)^2 with u = ln D0, r = (theta(o/sqrt D0) - theta_k) w_k
+      const double isq = rsqrt(D0);
+      double sc = 0.0, sg = 0.0, sh = 0.0;
+      for (int k = lane; k < m; k += 32) {
+        double th, dth;
+        const double x = o[k] * isq;
+        hermite_theta(K, nk, x, th, dth);
+        const double w = weight ? weight[k] : 1.0;
+        const double r = (th - theta[k]) * w;
+        const double ju = -0.5 * dth * x * w;
+        sc = fma(r, r, sc);
+        sg = fma(r, ju, sg);
+        sh = fma(ju, ju, sh);
+      }
+      c = warp_total(sc);
+      g = warp_total(sg);
+      h = warp_total(sh);
+    };
+    double D0 = 1.0;
+    int st = 0;
+    double c, g, h;
+    if (mode == 2) D0 = D0_io[j];
+    if (mode == 1) {
+      const double ratio = o[m - 1] / oi;  // fit.py:66: y0 = (o[-1]/original.oi)^2
+      double u = 2.0 * log(ratio > 0.0 ? ratio : 1.0);
+      double lam = 1e-3;
+      sums(exp(u), c, g, h);
+      st = 1;  // max_steps_reached unless the loop converges
+      for (int it = 0; it < 100; it++) {
+        if (!(h > 0.0)) { st = (g == 0.0) ? 0 : 2; break; }  // flat: nothing to fit / no direction
+        const double du = -g / (h * (1.0 + lam));
+        double c2, g2, h2;
+        sums(exp(u + du), c2, g2, h2);
+        if (c2 <= c) {
+          u += du;
+          const bool small = fabs(du) <= 1e-13 + 1e-11 * fabs(u) || (c - c2) <= 1e-16 * c;
+          c = c2; g = g2; h = h2;
+          lam = fmax(lam * 0.2, 1e-12);
+          if (small) { st = 0; break; }
+        } else {
+          lam *= 10.0;
+          if (lam > 1e12) { st = 0; break; }  // cannot decrease any further: at the minimum to rounding
+        }
+      }
+      D0 = exp(u);
+    } else {
+      sums(D0, c, g, h);
+    }
+    if (lane == 0) {
+      D0_io[j] = D0;
+      cost[j] = c / (double)m;
+      status[j] = st;
+    }
+  }
+}
+
 // ---- D, D', D'' at arbitrary theta (Solution.D for flux/sorptivity) ----------
 template <int MODEL>
 __device__ void diffusivity_one(const double* p, double th, double* out) {
@@ -586,6 +705,24 @@ int fx_eval_batch(int64_t n, const int32_t* counters, const double* knots, int32
   if (rc) return rc;
   eval_kernel<<<grid_for(n * q, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
       n, counters, knots, k_max, q, o_query, per_problem, theta, dtheta_do);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int fx_scaled_fit_batch(int64_t n, const int32_t* counters, const double* summary, const double* knots,
+                        int32_t k_max, int64_t m, const double* o, const double* theta, const double* weight,
+                        int32_t mode, double* D0, double* cost, int32_t* status, void* stream) {
+  if (n < 0 || m < 1 || k_max < 1 || mode < 0 || mode > 2) return fail(FX_ERR_ARG, "bad sizes or mode%s");
+  if (n == 0) return FX_OK;
+  if (m > 2147483647LL) return fail(FX_ERR_ARG, "too many data points%s");
+  if (!counters || !summary || !knots || !o || !theta || !D0 || !cost || !status)
+    return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  scaled_fit_kernel<<<grid_for(n * 32, 128, di.sms), 128, 0, (cudaStream_t)stream>>>(
+      n, counters, summary, knots, k_max, (int)m, o, theta, weight, mode, D0, cost, status);
   g_launches++;
   FX_CUDA(cudaGetLastError());
   return FX_OK;

@@ -141,6 +141,18 @@ int fx_eval_batch(int64_t n, const int32_t *counters /*[n][8]*/, const double *k
                   int64_t q, const double *o_query, int32_t per_problem, double *theta,
                   double *dtheta_do, void *stream);
 
+/* Replaces, for a batch of solved candidates, ScaledSolution.fitting_data (src/frontx/_inverse/fit.py:45-82:
+ * the one-parameter least-squares fit of D0 in theta(o/sqrt(D0)) to m data points) and the cost of fit()
+ * (:145-151: mean(((sol(o) - theta)/sigma)^2), inf for a candidate whose solve failed).
+ *   counters, summary, knots, k_max  as written by fx_solve_batch (dense output required)
+ *   o, theta [m], weight [m] = 1/sigma or NULL   the data, shared by all candidates
+ *   mode   0: D0 = 1;  1: fit D0 (start (o[m-1]/oi)^2, :66);  2: D0 given in D0[n] (e.g. from the sorptivity, :36-43)
+ *   D0 [n] in/out, cost [n], status [n] (0 converged, 1 max steps or failed solve, 2 no descent direction)
+ * All pointers device. */
+int fx_scaled_fit_batch(int64_t n, const int32_t *counters, const double *summary, const double *knots,
+                        int32_t k_max, int64_t m, const double *o, const double *theta, const double *weight,
+                        int32_t mode, double *D0, double *cost, int32_t *status, void *stream);
+
 /* D, dD/dtheta, d2D/dtheta2 at arbitrary theta (the callable the reference keeps
  * as Solution.D and uses in flux/sorptivity, src/frontx/_boltzmann.py:151-161).
  * theta is [n][q]; out is [n][q][3]. All pointers device. */
