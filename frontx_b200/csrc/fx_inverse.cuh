@@ -44,7 +44,7 @@
 
 namespace fx {
 
-constexpr int INV_BLOCK = 256;
+constexpr int INV_BLOCK = 128;
 constexpr int INV_ITEMS = 4;
 constexpr int INV_TILE = INV_BLOCK * INV_ITEMS;
 constexpr int INV_HALO_L = 2;
@@ -138,7 +138,7 @@ __device__ __forceinline__ void wait_load4(const double* src, double (&v)[4]) {
   }
 }
 
-__global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArgs A) {
+__global__ void __launch_bounds__(INV_BLOCK, 8) inverse_scan_kernel(const InvArgs A) {
   constexpr int NS = INV_TILE + INV_HALO_L + 2;  // points held: halo 2 left, 2 right (1 used + pad)
   __shared__ double s_th[NS], s_o[NS];
   __shared__ double s_d[2][INV_TILE + 1];  // do/dtheta at the tile's points; two buffers: a tile's
@@ -146,6 +146,9 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
   __shared__ double s_df[INV_TILE + 1];    // dtheta/do
   __shared__ double s_warp[2][INV_BLOCK / 32];
   __shared__ double s_scan[INV_ITEMS][INV_BLOCK / 32];
+  __shared__ double s_off[INV_ITEMS * (INV_BLOCK / 32) + 1];
+  constexpr int NWT = INV_ITEMS * (INV_BLOCK / 32);  // warp totals per tile
+  static_assert(NWT <= 32, "the warp totals of a tile are scanned by one warp");
   __shared__ double s_red[INV_NAGG];
   __shared__ unsigned long long s_ticket;
   __shared__ int s_bad;
@@ -188,36 +191,53 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       const double dir_step = th_g[n - 2] - th_g[n - 1];  // issued early: needed after the slopes
 
       // ---- load tile + halo in traversal order (r -> caller index n-1-r) ----
-      for (int q = tid; q < NS; q += INV_BLOCK) {
-        long long r = r0 - INV_HALO_L + q;
-        double a = 0.0, b = 0.0;
-        if (r >= 0 && r < n) {
-          long long j = n - 1 - r;
-          a = th_g[j];
-          b = o_g[j];
+      // s[q] holds traversal point r0 - 2 + q, i.e. memory index jtop - q with jtop = n+1-r0
+      {
+        const double* th_top = th_g + (n + 1 - r0);
+        const double* o_top = o_g + (n + 1 - r0);
+        if (r0 >= INV_HALO_L && r0 + INV_TILE + 2 <= n) {  // every point of tile and halo exists
+          for (int q = tid; q < NS; q += INV_BLOCK) {
+            s_th[q] = th_top[-q];
+            s_o[q] = o_top[-q];
+          }
+        } else {
+          const long long qlo = INV_HALO_L - r0, qhi = n + INV_HALO_L - r0;  // valid q in [qlo, qhi)
+          for (int q = tid; q < NS; q += INV_BLOCK) {
+            const bool ok = q >= qlo && q < qhi;
+            s_th[q] = ok ? th_top[-q] : 0.0;
+            s_o[q] = ok ? o_top[-q] : 0.0;
+          }
         }
-        s_th[q] = a;
-        s_o[q] = b;
       }
       __syncthreads();
 
       // ---- slopes do/dtheta (inverse interpolant) and dtheta/do (forward) at r in [r0, r0+TILE] --
       // Each lane forms the secants of the interval to the RIGHT of its point; the interval to the
       // left is the previous lane's (one shuffle; lane 0 of a warp recomputes it).
-      for (int e = tid; e < INV_TILE + INV_BLOCK; e += INV_BLOCK) {
-        const long long r = r0 + e;
+      const long long left = n - r0;                      // points of the profile from r0 on
+      const int npt = left > INV_TILE + 1 ? INV_TILE + 1 : (int)left;  // points e in [0, npt) exist
+      const bool first_tile = (r0 == 0);
+      const bool ends_here = left <= INV_TILE + 1;        // the profile's last point is e = npt-1
+      auto slope_at = [&](int e, bool shuffled) {
         const int q = e + INV_HALO_L;
-        const bool live = (e <= INV_TILE) && (r < n);
+        const bool live = e < npt;
+        const bool has_right = live && !(ends_here && e == npt - 1);
         double hx1 = 0.0, ho1 = 0.0, m1 = 0.0, mf1 = 0.0;  // interval (q, q+1)
-        if (live && r < n - 1) {
+        if (has_right) {
           hx1 = s_th[q + 1] - s_th[q];
           ho1 = s_o[q + 1] - s_o[q];
           m1 = ho1 * rcp_lean(hx1);
           mf1 = hx1 * rcp_lean(ho1);
         }
-        double hx0 = __shfl_up_sync(0xffffffffu, hx1, 1), ho0 = __shfl_up_sync(0xffffffffu, ho1, 1);
-        double m0 = __shfl_up_sync(0xffffffffu, m1, 1), mf0 = __shfl_up_sync(0xffffffffu, mf1, 1);
-        if (lane == 0 && live && r >= 1) {  // interval (q-1, q)
+        double hx0, ho0, m0, mf0;
+        if (shuffled) {
+          hx0 = __shfl_up_sync(0xffffffffu, hx1, 1);
+          ho0 = __shfl_up_sync(0xffffffffu, ho1, 1);
+          m0 = __shfl_up_sync(0xffffffffu, m1, 1);
+          mf0 = __shfl_up_sync(0xffffffffu, mf1, 1);
+        }
+        const bool has_left = live && !(first_tile && e == 0);
+        if ((!shuffled || lane == 0) && has_left) {  // interval (q-1, q)
           hx0 = s_th[q] - s_th[q - 1];
           ho0 = s_o[q] - s_o[q - 1];
           m0 = ho0 * rcp_lean(hx0);
@@ -225,28 +245,31 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
         }
         if (live) {
           double d, df;
-          if (two) {
-            d = (r == 0) ? m1 : m0;
-            df = (r == 0) ? mf1 : mf0;
-          } else if (r == 0) {  // one-sided: intervals (q, q+1) and (q+1, q+2)
+          if (has_left && has_right) {
+            d = pchip_interior_r(hx0, hx1, m0, m1, mf0, mf1);
+            df = pchip_interior_r(ho0, ho1, mf0, mf1, m0, m1);
+          } else if (two) {
+            d = has_right ? m1 : m0;
+            df = has_right ? mf1 : mf0;
+          } else if (has_right) {  // r == 0, one-sided: intervals (q, q+1) and (q+1, q+2)
             double hx2 = s_th[q + 2] - s_th[q + 1], ho2 = s_o[q + 2] - s_o[q + 1];
             d = pchip_edge(hx1, hx2, m1, ho2 / hx2);
             df = pchip_edge(ho1, ho2, mf1, hx2 / ho2);
-          } else if (r == n - 1) {  // one-sided, mirrored: intervals (q-1, q) and (q-2, q-1)
+          } else {  // r == n-1, one-sided, mirrored: intervals (q-1, q) and (q-2, q-1)
             double hxm = s_th[q - 1] - s_th[q - 2], hom = s_o[q - 1] - s_o[q - 2];
             d = pchip_edge(hx0, hxm, m0, hom / hxm);
             df = pchip_edge(ho0, hom, mf0, hxm / hom);
-          } else {
-            d = pchip_interior_r(hx0, hx1, m0, m1, mf0, mf1);
-            df = pchip_interior_r(ho0, ho1, mf0, mf1, m0, m1);
           }
           sd[e] = d;
           s_df[e] = df;
-        } else if (e <= INV_TILE) {
+        } else {
           sd[e] = 0.0;
           s_df[e] = 0.0;
         }
-      }
+      };
+#pragma unroll
+      for (int it = 0; it < INV_ITEMS; it++) slope_at(it * INV_BLOCK + tid, true);
+      if (tid == 0) slope_at(INV_TILE, false);  // the point that closes the tile's last interval
       __syncthreads();
 
       // ---- per-interval integrals and the block scan (one barrier) -----------------
@@ -281,19 +304,17 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       }
       if (bad) atomicOr(&s_bad, 1);
       __syncthreads();
-      double carry = 0.0;
-#pragma unroll
-      for (int it = 0; it < INV_ITEMS; it++) {
-        double woff = 0.0, wtot = 0.0;
-#pragma unroll
-        for (int w = 0; w < INV_BLOCK / 32; w++) {
-          double v = s_scan[it][w];
-          if (w < (int)wid) woff += v;
-          wtot += v;
-        }
-        excl[it] = carry + woff + (incl[it] - mine[it]);
-        carry += wtot;
+      // exclusive offsets of the ITEMS x 8 warp totals (item-major = traversal order): one warp scans them
+      if (wid == 0) {
+        const double v = ((int)lane < NWT) ? (&s_scan[0][0])[lane] : 0.0;
+        const double inc = warp_incl_scan(v, lane);
+        if ((int)lane < NWT) s_off[lane] = inc - v;
+        if (lane == 31) s_off[NWT] = inc;
       }
+      __syncthreads();
+      const double carry = s_off[NWT];
+#pragma unroll
+      for (int it = 0; it < INV_ITEMS; it++) excl[it] = s_off[it * (INV_BLOCK / 32) + wid] + (incl[it] - mine[it]);
 
       // ---- publish the tile aggregate; close the group if this is its last tile to arrive ------
       if (wid == 0) {
@@ -364,17 +385,19 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       const long long r0 = t2 * INV_TILE;
       const double* sd = s_d[pv_buf];
 
-      // D at the tile's points, caller order
+      // D at the tile's points, caller order: traversal point r0 + e is memory index top - e
+      const long long top = p2 * n + (n - 1 - r0);
+      const long long left = n - r0;
+      const int npt = left > INV_TILE ? INV_TILE : (int)left;
+      double* D_top = A.D + top;
 #pragma unroll
       for (int it = 0; it < INV_ITEMS; it++) {
-        int e = it * INV_BLOCK + tid;
-        long long r = r0 + e;
-        if (r < n) {
-          double Iod = prefix + pv_excl[it];
-          long long j = p2 * n + (n - 1 - r);
-          A.D[j] = -(sd[e] * Iod) * 0.5;
-          if (A.slope) A.slope[j] = sd[e];
-          if (A.anti) A.anti[j] = Iod;
+        const int e = it * INV_BLOCK + tid;
+        if (e < npt) {
+          const double Iod = prefix + pv_excl[it];
+          D_top[-e] = -(sd[e] * Iod) * 0.5;
+          if (A.slope) A.slope[top - e] = sd[e];
+          if (A.anti) A.anti[top - e] = Iod;
         }
       }
 
