@@ -15,15 +15,15 @@
 // with SIGNED steps, which is term-by-term the sorted-order formula for a
 // decreasing profile and its exact mirror for an increasing one.
 //
-// HBM-bound: 16 B/point read (o, theta), 8 B/point written (D); every point is
-// read once (plus a 3-point halo per tile).  One CTA owns a tile of TILE
-// consecutive points of one profile:
+// Algorithmic traffic: 16 B/point read (o, theta), 8 B/point written (D); every point is
+// read once (plus a 3-point halo per tile), measured DRAM traffic equals it.  One CTA owns a tile
+// of TILE consecutive points of one profile:
 //   load tile+halo (coalesced) -> shared memory
 //   PCHIP slopes of o(theta) and of theta(o) for the tile (3-point stencils)
 //   per-interval integrals; block scan (warp shuffles) of the inverse ones
-//   publish the tile aggregate, then sum the aggregates of all EARLIER tiles of
-//   the profile in a fixed order (tickets are handed out in order, so every
-//   earlier tile is resident or finished: no deadlock, no serial chain, and the
+//   publish the tile aggregate, go on to the next tile, then add up the aggregates of all
+//   EARLIER tiles of the profile in a fixed two-level order (tickets are handed out in order,
+//   so every earlier tile is resident or finished: no deadlock, no serial chain, and the
 //   result is bit-reproducible run to run)
 //   D = -d * (prefix + local)/2, written coalesced in the caller's point order.
 //

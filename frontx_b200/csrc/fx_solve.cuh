@@ -19,10 +19,11 @@
 //     lane pops a shot, integrates it, folds the residual into that problem's bisection,
 //     pushes the problem's next shot and pops the oldest waiting one (FIFO, so all problems
 //     advance at the same rate and finish together).
-//   * Speculative bisection: when fewer problems remain than lanes/3, the next 2..5 levels of
+//   * Speculative bisection: when fewer problems remain than lanes, the next 2..5 levels of
 //     a problem's bisection tree (3..31 midpoints, each a pure function of the bracket) are
-//     pushed as independent shots; whoever finishes the last of them walks the tree with the
-//     real residuals, consuming up to 5 bisection steps per round.  Results, counters and the
+//     pushed as independent shots, sized so that the batches of all unfinished problems just
+//     fill the lanes; whoever finishes the last shot of a batch walks the tree with the real
+//     residuals, consuming up to 5 bisection steps per round.  Results, counters and the
 //     accepted d_dob are identical to sequential bisection (only shots on the taken path are
 //     counted); the wasted shots run on lanes that had nothing else to do.  This is what
 //     shortens the critical path of the failing problems from ~55 sequential shots to ~25.
@@ -31,9 +32,12 @@
 //     1/D -- and D'' on the trip that also builds the chord Jacobian), so lanes in different
 //     stages, steps, shots or problems execute the expensive model evaluation convergently;
 //     everything else is a short predicated block after it.
-//   * The 7 stage derivatives live in shared memory, one column per thread (conflict-free),
-//     because the stage index is a per-lane runtime value; the Butcher tableau, predictor rows
-//     and the log/exp lookup tables sit beside them.
+//   * Parking: a lane whose six stages converged waits up to WAIT_TRIPS trips for WAIT_QUORUM
+//     lanes of its warp, so that the ~200-instruction attempt-end block runs for groups.
+//   * Registers bound the resident warps: the 7 stage derivatives (the stage index is a per-lane
+//     runtime value), the model constants and every per-lane value that is not needed on each
+//     trip live in shared memory, one column per thread (conflict-free), beside the Butcher
+//     tableau, the predictor rows and the log/exp lookup tables: 96 registers, 5 CTAs per SM.
 //   * Kernels are compiled per model (template parameter); mixed batches are bucketed by
 //     model on the device (fx_api.cu) and each bucket has its own queue.
 //   * Output: 64-byte summary + 32-byte counter record per problem, and one 32-byte knot
@@ -53,7 +57,7 @@
 namespace fx {
 
 constexpr int SOLVE_BLOCK = 128;
-constexpr int SOLVE_CTAS_PER_SM = 5;             // 128 registers per thread: 4 warps per SM sub-partition
+constexpr int SOLVE_CTAS_PER_SM = 5;             // <= 96 registers per thread: 5 warps per SM sub-partition
 constexpr int SPEC_MAX_DEPTH = 5;                // up to 31 speculative shots per problem
 constexpr int SPEC_NODES = 1 << SPEC_MAX_DEPTH;  // entries per speculation slot (entry 0 = header)
 constexpr int FX_IN_FLIGHT = -3;                 // counters[.][0] while a problem is unfinished: if a launch ever
