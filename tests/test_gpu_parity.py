@@ -327,8 +327,21 @@ def test_host_entry_point_matches_device_entry_point(paper):
 
 
 # ---------------------------------------------------------------------------
-# full-size properties (BASELINE sizes; no oracle needed)
+# full size (BASELINE config C2): bit equality with the twin, then properties
 # ---------------------------------------------------------------------------
+def test_full_size_bitwise_vs_twin_c2(fxo):
+    """All 10^5 problems of the benchmark's own workload: the shot queue, the speculative bisection of
+    the end phase and the replay of repeated shots give the twin's summaries and counters bit for bit
+    (the twin needs ~15 s on the box's host cores)."""
+    import bench
+
+    mb = bench.c2_workload(100_000, seed=0)
+    tw = fxo.twin_solve_batch(mb.model_id, mb.params, bench.B_BOUNDARY, bench.I_INITIAL)
+    sol = fx.solve_batch(mb, b=bench.B_BOUNDARY, i=bench.I_INITIAL, k_max=0, throw=False)
+    np.testing.assert_array_equal(sol.counters.cpu().numpy(), tw["counters"])
+    np.testing.assert_array_equal(sol.summary.cpu().numpy().view(np.int64), tw["summary"].view(np.int64))
+
+
 def test_full_size_properties_c2():
     n = 100_000
     models = vg_sweep(n)
