@@ -137,6 +137,22 @@ def ncu_dram_bytes_per_launch(n: int):
     return total or None
 
 
+def ncu_pipe_utilisation(n: int):
+    """FP64-pipe and issue utilisation of the dominant kernel from the committed ncu capture (percent of
+    cycles; measured under ncu at 10^5 problems per launch, so informative only); None for other sizes."""
+    path = ROOT / "profiles" / "r1_vg_kernel_ncu_raw_n100k.txt"
+    if n != 100_000 or not path.exists():
+        return None
+    want = {"sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_active_pct",
+            "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct"}
+    out = {}
+    for line in path.read_text().splitlines():
+        f = line.split()
+        if len(f) == 3 and f[0] in want:
+            out[want[f[0]]] = float(f[2])
+    return out or None
+
+
 def cpu_arm(models, n_sample: int, threads: int):
     """Time the oracle (CPU restatement of the reference algorithm) on the first n_sample problems."""
     from oracle import fxo
@@ -290,6 +306,7 @@ def run_ours(args) -> None:
         "bound": "fp64", "kernel": "fx::shoot_bisect_kernel<van_genuchten>",
         "achieved": achieved / 1e12, "peak": peak.value / 1e12, "unit": "TFLOP/s",
         "frac": achieved / peak.value, "traffic": ncu_dram_bytes_per_launch(n),
+        "ncu": ncu_pipe_utilisation(n),
         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops,
         "algorithmic_flops_per_solve": flops / n,
         "hbm_gbs": n * (BYTES_IN + BYTES_OUT) / (k_ms * 1e-3) / 1e9,
