@@ -53,6 +53,19 @@ def test_argument_errors_without_a_device():
     assert L.fx_solve_batch(4, None, None, None, None, None, None, None, 0, None, None) == -1
     assert L.fx_inverse_batch(1, 1, None, None, None, None, None, None, None, None) == -1
     assert L.fx_solve_batch(0, None, None, None, None, None, None, None, 0, None, None) == 0
+    # flow-rate boundary: needs q and a bracket, and a radial geometry
+    assert L.fx_solve_flowrate_batch(3, None, None, None, None, None, None, None, None, None, 0, None, None) == -1
+    planar = _lib.default_options()
+    dummy = ctypes.c_void_p(8)
+    assert L.fx_solve_flowrate_batch(3, dummy, dummy, dummy, dummy, dummy, dummy, planar, dummy, dummy, 0, None,
+                                     None) == -1
+    assert b"radial" in L.fx_last_error()
+    assert L.fx_solve_flowrate_batch(0, None, None, None, None, None, None, None, None, None, 0, None, None) == 0
+    # batched D0 fit: mode in {0, 1, 2}, at least one data point, dense output required
+    assert L.fx_scaled_fit_batch(2, dummy, dummy, dummy, 8, 5, dummy, dummy, None, 3, dummy, dummy, dummy, None) == -1
+    assert L.fx_scaled_fit_batch(2, dummy, dummy, dummy, 8, 0, dummy, dummy, None, 1, dummy, dummy, dummy, None) == -1
+    assert L.fx_scaled_fit_batch(2, dummy, dummy, None, 8, 5, dummy, dummy, None, 1, dummy, dummy, dummy, None) == -1
+    assert L.fx_scaled_fit_batch(0, None, None, None, 8, 5, None, None, None, 1, None, None, None, None) == 0
 
 
 def test_no_cpu_fallback():
