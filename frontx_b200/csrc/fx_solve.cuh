@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
   constexpr bool FLOW = GEOM == 2;
   __shared__ Tableau tab;
   __shared__ MathTab mt;                     // log / exp lookup tables (lanes index them divergently)
-  __shared__ double fsm[7][2][SOLVE_BLOCK];  // stage derivatives, one column per thread
+  __shared__ __align__(16) double fsm[7][SOLVE_BLOCK][2];  // stage derivatives: one 16-byte pair per stage and thread
   // Per-lane state that is not needed on every trip lives in shared memory (one column per
   // thread, conflict-free) so that the registers hold only the hot integrator state:
   // registers, not arithmetic, bound the resident warps of this kernel.
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
   const unsigned FULL = 0xffffffffu;
   const Tol tol = {A.rtol, A.atol};
   const int radial_k = RADIAL ? A.radial_k : 0;
-  auto fs = [&](int j, int c) -> double { return fsm[j][c][tid]; };
+  auto fs = [&](int j, int c) -> double { return fsm[j][tid][c]; };
 
   // bucket geometry: model `slot` owns perm[off .. off+n_work) and a ring region of its own
   // A mixed batch runs one persistent grid per model side by side: each keeps a share of its
@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     } else if (mode == M_INIT0) {
       // solver.init + first half of the Hairer initial-step heuristic
       rhs_shot++;
-      fsm[0][0][tid] = R.F0;
-      fsm[0][1][tid] = R.F1;
+      fsm[0][tid][0] = R.F0;
+      fsm[0][tid][1] = R.F1;
       if (A.knots && node == 0 && A.k_max > 0)
         *reinterpret_cast<double4*>(A.knots + (size_t)prob * A.k_max * FX_KNOT) = make_double4(t0, y00, y01, R.F1);
       n_knots = 1;
@@ -465,8 +465,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       dsz = size;
       if (done) {
         if (ok) {
-          fsm[stage][0][tid] = f0;
-          fsm[stage][1][tid] = f1;
+          fsm[stage][tid][0] = f0;
+          fsm[stage][tid][1] = f1;
           if (stage < 6) { stage++; prep = true; }
           else { mode = M_WAIT; iter = 0; }  // iter counts the trips parked
         } else {
@@ -505,8 +505,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
         t0 = t1;
         y00 = s.y10;
         y01 = s.y11;
-        fsm[0][0][tid] = f0;  // FSAL
-        fsm[0][1][tid] = f1;
+        fsm[0][tid][0] = f0;  // FSAL
+        fsm[0][tid][1] = f1;
         if (A.knots && node == 0 && n_knots < A.k_max) {
           double* knot_row = A.knots + (size_t)prob * A.k_max * FX_KNOT;
           *reinterpret_cast<double4*>(knot_row + (size_t)n_knots * FX_KNOT) = make_double4(t0, y00, y01, f1);
