@@ -96,6 +96,72 @@ def solve_batch_distributed(models: ModelBatch, *, b: Any, i: Any, itol: float =
             gather_records(counters, n, world, rank, block, group), mine)
 
 
+def profile_slice(batch: int, rank: int, world: int) -> slice:
+    """Contiguous profiles owned by ``rank`` (C5 shards by profile: 125 of 10^3 per GPU on 8 GPUs)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    per, extra = divmod(batch, world)
+    start = rank * per + min(rank, extra)
+    return slice(start, start + per + (1 if rank < extra else 0))
+
+
+def inverse_distributed(o: Any, theta: Any, *, gather_D: bool = False, group: Any = None,  # noqa: N803
+                        local_inverse: Callable | None = None):
+    """Profile -> D(theta) for ``[batch, npts]`` profiles across all ranks of the default process group.
+
+    Every rank passes the SAME global arrays (numpy); rank r inverts ``profile_slice(batch, r, world)`` on its
+    own GPU.  Profiles are independent, so nothing is exchanged on the data path; the per-profile sorptivity
+    and status records (and, with ``gather_D=True``, the D arrays: 8 bytes per point) are all-gathered.
+    Returns ``(D, sorptivity[batch], status[batch], my_slice)`` with ``D`` the local ``[n_local, npts]``
+    tensor unless gathered.  ``local_inverse(o, theta) -> (D, sorptivity, status)`` tensors lets the CPU tests
+    run the sharding and the collective without a GPU; the default is the CUDA path.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    o = np.asarray(o, dtype=np.float64)
+    theta = np.asarray(theta, dtype=np.float64)
+    if o.ndim != 2 or o.shape != theta.shape:
+        raise ValueError("o and theta must have the same [batch, npts] shape")
+    batch, npts = o.shape
+    mine = profile_slice(batch, rank, world)
+    if local_inverse is None:
+        from ._inverse import inverse
+
+        if mine.stop > mine.start:
+            res = inverse(o[mine], theta[mine], throw=False)
+            D, sorp, status = res.D_at_knots, res.sorptivity(), res.status
+        else:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            D = torch.empty((0, npts), dtype=torch.float64, device=dev)
+            sorp = torch.empty((0,), dtype=torch.float64, device=dev)
+            status = torch.empty((0,), dtype=torch.int32, device=dev)
+    else:
+        D, sorp, status = local_inverse(o[mine], theta[mine])
+    pad = -(-batch // world)
+
+    def gather(local, width):
+        send = torch.zeros((pad, width), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local.reshape(local.shape[0], width)
+        recv = torch.empty((world * pad, width), dtype=local.dtype, device=local.device)
+        if world == 1:
+            recv.copy_(send)
+        else:
+            dist.all_gather_into_tensor(recv, send, group=group)
+        parts = []
+        for r in range(world):
+            sl = profile_slice(batch, r, world)
+            parts.append(recv[r * pad: r * pad + (sl.stop - sl.start)])
+        return torch.cat(parts)
+
+    sorp_all = gather(sorp, 1).reshape(batch)
+    status_all = gather(status, 1).reshape(batch)
+    D_out = gather(D, npts) if gather_D else D
+    return D_out, sorp_all, status_all, mine
+
+
 def init_from_env(backend: str | None = None):
     """Initialise torch.distributed from torchrun's environment (RANK, WORLD_SIZE, LOCAL_RANK)."""
     import os

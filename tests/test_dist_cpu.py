@@ -78,3 +78,66 @@ def test_two_rank_gather_matches_single_process(tmp_path, fxo):
     mine = [np.load(tmp_path / f"mine{r}.npy") for r in range(world)]
     assert sorted(np.concatenate(mine).tolist()) == list(range(n))
     assert mine[0].tolist() == [0, 1, 2, 6, 7, 8, 12, 13]
+
+
+def test_profile_slices_partition():
+    for batch, world in [(1000, 8), (10, 3), (2, 4), (0, 2), (7, 7)]:
+        sls = [_dist.profile_slice(batch, r, world) for r in range(world)]
+        covered = [j for sl in sls for j in range(sl.start, sl.stop)]
+        assert covered == list(range(batch))
+        sizes = [sl.stop - sl.start for sl in sls]
+        assert max(sizes) - min(sizes) <= 1
+    assert _dist.profile_slice(1000, 3, 8) == slice(375, 500)  # C5: 125 profiles per GPU
+
+
+def _inverse_worker(rank: int, world: int, port: int, out_dir: str) -> None:
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    from oracle import fxo
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o, theta = _inverse_profiles()
+
+    def oracle_inverse(oo, th):
+        D, S, st = [], [], []
+        for j in range(oo.shape[0]):
+            rc, Dk, s1, _ = fxo.inverse(oo[j], th[j])
+            D.append(Dk)
+            S.append(s1)
+            st.append(rc)
+        return (torch.from_numpy(np.array(D).reshape(len(D), oo.shape[1])), torch.tensor(S, dtype=torch.float64),
+                torch.tensor(st, dtype=torch.int32))
+
+    D, sorp, status, mine = _dist.inverse_distributed(o, theta, gather_D=True, local_inverse=oracle_inverse)
+    np.save(os.path.join(out_dir, f"invD{rank}.npy"), D.numpy())
+    np.save(os.path.join(out_dir, f"invS{rank}.npy"), sorp.numpy())
+    np.save(os.path.join(out_dir, f"invM{rank}.npy"), np.array([mine.start, mine.stop]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _inverse_profiles():
+    a = np.array([0.5, 0.8, 1.0, 1.3, 2.0])
+    o = np.linspace(0, 20, 400)[None, :] / a[:, None]
+    return o, np.exp(-a[:, None] * o)
+
+
+def test_two_rank_inverse_matches_single_process(tmp_path, fxo):
+    import torch.multiprocessing as mp
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = 2
+    mp.spawn(_inverse_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    o, theta = _inverse_profiles()
+    ref_D = np.array([fxo.inverse(o[j], theta[j])[1] for j in range(o.shape[0])])
+    ref_S = np.array([fxo.inverse(o[j], theta[j])[2] for j in range(o.shape[0])])
+    for r in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / f"invD{r}.npy"), ref_D)
+        np.testing.assert_array_equal(np.load(tmp_path / f"invS{r}.npy"), ref_S)
+    assert np.load(tmp_path / "invM0.npy").tolist() == [0, 3] and np.load(tmp_path / "invM1.npy").tolist() == [3, 5]
