@@ -106,8 +106,8 @@ __device__ __forceinline__ double pchip_interior_r(double h0, double h1, double 
   double w1 = fma(2.0, h1, h0);
   double w2 = fma(2.0, h0, h1);
   double v = (w1 + w2) * rcp_lean(fma(w1, im0, w2 * im1));
-  bool same = ((m0 > 0.0) && (m1 > 0.0)) || ((m0 < 0.0) && (m1 < 0.0));
-  return same ? v : 0.0;
+  // same strict sign <=> positive product (secants are O(1e-9 .. 1e9) here: no underflow to zero)
+  return (m0 * m1 > 0.0) ? v : 0.0;
 }
 
 __device__ __forceinline__ double warp_incl_scan(double v, unsigned lane) {
