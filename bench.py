@@ -207,7 +207,6 @@ def run_ours(args) -> None:
     import torch
     import torch.distributed as dist
 
-    import frontx_b200 as fx
     from frontx_b200 import _dist, _lib
 
     rank, world, local = _dist.init_from_env()

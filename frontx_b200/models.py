@@ -16,7 +16,7 @@ there is no CPU implementation in this package.
 
 from __future__ import annotations
 
-from dataclasses import dataclass, fields
+from dataclasses import dataclass
 from typing import Any, Sequence
 
 import numpy as np
