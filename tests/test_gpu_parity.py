@@ -23,6 +23,7 @@ import pytest
 from conftest import B_PAPER, I_PAPER, mixed_sweep, paper_models, vg_sweep
 
 import frontx_b200 as fx
+from frontx_b200 import models as M
 from frontx_b200 import _lib
 
 pytestmark = pytest.mark.gpu
@@ -269,6 +270,52 @@ def test_speculative_and_sequential_bisection_agree(fxo):
     tw = fxo.twin_solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER)
     np.testing.assert_array_equal(spec.summary.cpu().numpy(), tw["summary"])
     np.testing.assert_array_equal(spec.counters.cpu().numpy(), tw["counters"])
+
+
+def test_all_models_random_batch_bitwise_vs_twin(fxo):
+    """Every model id in one batch, random parameters and boundary values -- wetting and drying
+    (i > b), bracket expansions (constant and mildly nonlinear D), failures -- through the shot queue
+    with speculation (k_max = 0) and without (k_max > 0): summaries, counters and knots equal the twin's."""
+    rng = np.random.default_rng(21)
+    ms, bs, is_ = [], [], []
+    for _ in range(60):
+        ms.append(M.LETd(L=rng.uniform(0.01, 1.5), E=10 ** rng.uniform(3, 4.3), T=rng.uniform(1.0, 1.6),
+                         Dwt=10 ** rng.uniform(-4, -2.7), theta_range=(0.0198, 0.7)))
+        bs.append(0.7 - 10 ** rng.uniform(-7, -2)); is_.append(rng.uniform(0.021, 0.3))
+        ms.append(M.BrooksAndCorey(n=rng.uniform(0.2, 0.6), l=rng.uniform(1, 5), Ks=10 ** rng.uniform(-6, -5),
+                                   theta_range=(2.378e-5, 0.7)))
+        bs.append(rng.uniform(0.4, 0.7)); is_.append(rng.uniform(0.01, 0.2))
+        ms.append(M.VanGenuchten(n=rng.uniform(1.5, 9), l=0.5, Ks=10 ** rng.uniform(-7, -4), alpha=rng.uniform(0.5, 5),
+                                 theta_range=(0.005, 0.7)))
+        bs.append(0.7 - 10 ** rng.uniform(-7, -1)); is_.append(rng.uniform(0.006, 0.3))
+        ms.append(M.LETxs(Lw=rng.uniform(1, 2.5), Ew=10 ** rng.uniform(1.5, 2.7), Tw=rng.uniform(0.7, 1.2),
+                          Ls=rng.uniform(0.3, 0.8), Es=10 ** rng.uniform(2, 3), Ts=rng.uniform(0.3, 0.6),
+                          Ks=10 ** rng.uniform(-3, -1.5), theta_range=(0.01176, 0.7)))
+        bs.append(0.7 - 10 ** rng.uniform(-7, -2)); is_.append(rng.uniform(0.02, 0.2))
+        ms.append(fx.D.power_law(k=rng.uniform(0.5, 6), a=rng.uniform(0.5, 2), epsilon=rng.choice([0.0, 1e-3])))
+        bs.append(rng.uniform(0.5, 1.5)); is_.append(rng.uniform(0.01, 0.3))
+        ms.append(fx.D.constant(10 ** rng.uniform(-3, 1)))
+        bs.append(rng.uniform(-1, 1)); is_.append(rng.uniform(-1, 1))  # either direction, needs expansions
+        ms.append(M.LogDiffusivity(c0=rng.uniform(0.4, 1.0), c1=-rng.uniform(0.1, 0.5)))
+        bs.append(1.0); is_.append(rng.uniform(0.0, 0.3))
+        ms.append(M.LETd(L=rng.uniform(0.01, 1.5), E=10 ** rng.uniform(3, 4.3), T=1.3, Dwt=1e-3,
+                         theta_range=(0.0198, 0.7)))
+        bs.append(rng.uniform(0.03, 0.2)); is_.append(rng.uniform(0.4, 0.69))  # wetting front reversed
+    for _ in range(4):  # the reference's unsolvable case (tests/test_solve.py:148-156) a few times over
+        ms.append(fx.D.power_law(k=1))
+        bs.append(1.0); is_.append(-1.0)
+    models = fx.ModelBatch.from_models(ms)
+    b, i = np.array(bs), np.array(is_)
+    tw = fxo.twin_solve_batch(models.model_id, models.params, b, i, k_max=600)
+    assert (tw["counters"][:, 2] > 0).sum() >= 30 and (tw["counters"][:, 0] != 0).sum() >= 4  # expansions, failures
+    spec = fx.solve_batch(models, b=b, i=i, k_max=0, throw=False)
+    seq = fx.solve_batch(models, b=b, i=i, k_max=600, throw=False)
+    for sol in (spec, seq):
+        np.testing.assert_array_equal(sol.counters.cpu().numpy(), tw["counters"])
+        got, want = sol.summary.cpu().numpy(), tw["summary"]
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        np.testing.assert_array_equal(got[~np.isnan(want)].view(np.int64), want[~np.isnan(want)].view(np.int64))
+    np.testing.assert_array_equal(seq.knots.cpu().numpy(), tw["knots"])
 
 
 def test_empty_and_single():
