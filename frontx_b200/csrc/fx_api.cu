@@ -749,7 +749,7 @@ int fx_inverse_batch(int64_t batch, int64_t npts, const double* o, const double*
   if (batch < 0 || npts < 0) return fail(FX_ERR_ARG, "bad sizes%s");
   if (batch == 0) return FX_OK;
   if (npts < 2) return fail(FX_ERR_ARG, "a profile needs at least 2 points%s");
-  if (!o || !theta || !D_at_knots || !sorptivity || !status)
+  if (!o || !theta || !D_at_knots || !status)
     return fail(FX_ERR_ARG, "null pointer argument%s");
   DeviceInfo di;
   int rc = device_info(&di);

@@ -16,24 +16,25 @@
 // decreasing profile and its exact mirror for an increasing one.
 //
 // Algorithmic traffic: 16 B/point read (o, theta), 8 B/point written (D); every point is
-// read once (plus a 3-point halo per tile), measured DRAM traffic equals it.  One CTA owns a tile
-// of TILE consecutive points of one profile:
-//   load tile+halo (coalesced) -> shared memory
-//   PCHIP slopes of o(theta) and of theta(o) for the tile (3-point stencils)
-//   per-interval integrals; block scan (warp shuffles) of the inverse ones
+// read once (plus a 3-point halo per thread, which hits L1).  One CTA owns a tile of INV_TILE
+// consecutive points of one profile, one THREAD a chunk of INV_ITEMS consecutive points, held in
+// registers from the 16-byte global loads to the 16-byte global stores (no shared-memory staging):
+//   steps (d theta, d o) of the chunk's intervals and the two either side
+//   PCHIP slope do/dtheta at the chunk's points (and dtheta/do when the sorptivity is wanted)
+//   per-interval cubic-Hermite integrals; running sum in the thread, one warp scan of the thread
+//   totals, the four warp totals through shared memory
 //   publish the tile aggregate, go on to the next tile, then add up the aggregates of all
 //   EARLIER tiles of the profile in a fixed two-level order (tickets are handed out in order,
 //   so every earlier tile is resident or finished: no deadlock, no serial chain, and the
 //   result is bit-reproducible run to run)
-//   D = -d * (prefix + local)/2, written coalesced in the caller's point order.
+//   D = -d * (prefix + local)/2, written in the caller's point order.
 //
 // Arithmetic: an fp64 division costs ~25 issue slots on sm_100a (scripts/ubench_fp64.cu), and
 // scipy's formulas written literally take 12 per point, which made the first version of this
-// kernel issue-bound at 13 % of the HBM roofline.  Here every interval's two secants
-// (do/dtheta and dtheta/do, reciprocals of one another) are formed once, by the branch-free
-// reciprocal of fx_math.cuh, and shared with the neighbouring point through a warp shuffle; the
-// harmonic mean of the interior slope, 1/((w1/m0 + w2/m1)/(w1+w2)), becomes
-// (w1+w2)/(w1*im0 + w2*im1) with im the other direction's secant: 4 reciprocals per point.
+// kernel issue-bound at 13 % of the HBM roofline; the second (secants shared through shuffles,
+// striped shared-memory tile, 4 reciprocals per point) reached 21 % at 363 instructions per point.
+// Here the harmonic mean is cleared of its divisions algebraically (pchip_interior_steps): ONE
+// reciprocal per point and slope, no secant formed, no shuffle outside the scan.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -45,9 +46,9 @@
 namespace fx {
 
 constexpr int INV_BLOCK = 128;
-constexpr int INV_ITEMS = 4;
-constexpr int INV_TILE = INV_BLOCK * INV_ITEMS;
-constexpr int INV_HALO_L = 2;
+constexpr int INV_ITEMS = 8;                      // consecutive points owned by one thread
+constexpr int INV_TILE = INV_BLOCK * INV_ITEMS;   // 1024 points per tile
+constexpr int INV_NW = INV_BLOCK / 32;
 constexpr int INV_NAGG = 4;  // inverse integral, forward PCHIP integral, trapezoid, flagged-bad count
 constexpr int INV_GROUP = 32; // tiles per look-back group (one warp reads a group)
 
@@ -56,7 +57,7 @@ struct InvArgs {
   const double* o;                    // [batch][npts]
   const double* theta;                // [batch][npts]
   double* D;                          // [batch][npts]
-  double* sorp;                       // [batch][4]: PCHIP Int theta do, trapezoid Int theta do, extrapolated Int_0^o0, spare
+  double* sorp;                       // [batch][4]: PCHIP Int theta do, trapezoid Int theta do, extrapolated Int_0^o0, spare; or nullptr
   int* status;                        // [batch]
   double* slope;                      // [batch][npts] do/dtheta at the knots, or nullptr
   double* anti;                       // [batch][npts] Int_i^theta o dtheta at the knots, or nullptr
@@ -86,28 +87,29 @@ __device__ __forceinline__ double pchip_edge(double h0, double h1, double m0, do
   return d;
 }
 
-// 1/x by the hardware seed and two Newton steps (correctly rounded for ordinary arguments; a
-// zero or non-finite step only occurs in a profile that is flagged non-monotone anyway)
+// 1/x: hardware seed (relative error 2^-23) and one cubic correction, y(1 + e + e^2): the remaining
+// error, e^3 plus two roundings, is below 1.5 ulp.  A zero or non-finite argument gives inf/NaN,
+// which every caller discards by a select.
 __device__ __forceinline__ double rcp_lean(double x) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   double e = fma(-x, y, 1.0);
   e = fma(e, e, e);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
   return fma(y, e, y);
 }
 
-// interior slope from the two secants m0, m1 and their reciprocals im0, im1 (the secants of the
-// inverse function): scipy's weighted harmonic mean with one reciprocal; zero unless the secants
-// have the same strict sign
-__device__ __forceinline__ double pchip_interior_r(double h0, double h1, double m0, double m1, double im0,
-                                                   double im1) {
-  double w1 = fma(2.0, h1, h0);
-  double w2 = fma(2.0, h0, h1);
-  double v = (w1 + w2) * rcp_lean(fma(w1, im0, w2 * im1));
-  // same strict sign <=> positive product (secants are O(1e-9 .. 1e9) here: no underflow to zero)
-  return (m0 * m1 > 0.0) ? v : 0.0;
+// Interior PCHIP slope of y(x) at a point from the steps either side, (h0, g0) = (dx, dy) of the
+// interval before it and (h1, g1) of the one after.  scipy's weighted harmonic mean
+//   (w1 + w2) / (w1/m0 + w2/m1),  m = g/h,  w1 = 2 h1 + h0,  w2 = h1 + 2 h0
+// cleared of its three divisions: (w1 + w2) g0 g1 / (w1 h0 g1 + w2 h1 g0) -- one reciprocal per point
+// and no secant is ever formed.  `same` says the two secants have the same strict sign.
+__device__ __forceinline__ double pchip_interior_steps(double h0, double g0, double h1, double g1, bool same) {
+  const double w1 = fma(2.0, h1, h0);
+  const double w2 = fma(2.0, h0, h1);
+  const double num = ((w1 + w2) * g0) * g1;
+  const double den = fma(w2 * h1, g0, (w1 * h0) * g1);
+  const double v = num * rcp_lean(den);
+  return same ? v : 0.0;
 }
 
 __device__ __forceinline__ double warp_incl_scan(double v, unsigned lane) {
@@ -138,17 +140,142 @@ __device__ __forceinline__ void wait_load4(const double* src, double (&v)[4]) {
   }
 }
 
-__global__ void __launch_bounds__(INV_BLOCK, 8) inverse_scan_kernel(const InvArgs A) {
-  constexpr int NS = INV_TILE + INV_HALO_L + 2;  // points held: halo 2 left, 2 right (1 used + pad)
-  __shared__ double s_th[NS], s_o[NS];
-  __shared__ double s_d[2][INV_TILE + 1];  // do/dtheta at the tile's points; two buffers: a tile's
-                                           // output is written one tile later (see below)
-  __shared__ double s_df[INV_TILE + 1];    // dtheta/do
-  __shared__ double s_warp[2][INV_BLOCK / 32];
-  __shared__ double s_scan[INV_ITEMS][INV_BLOCK / 32];
-  __shared__ double s_off[INV_ITEMS * (INV_BLOCK / 32) + 1];
-  constexpr int NWT = INV_ITEMS * (INV_BLOCK / 32);  // warp totals per tile
-  static_assert(NWT <= 32, "the warp totals of a tile are scanned by one warp");
+// What one thread makes of its INV_ITEMS consecutive points, all in registers.  Traversal point
+// j = 0..7 of the thread is profile traversal index rb + j, memory index n-1-rb-j.
+//   d[j], df[j]   do/dtheta and dtheta/do at point j = 0..8 (8 closes the thread's last interval)
+//   I[j]          Int o dtheta over the interval (j, j+1), j = 0..7
+//   sumF, sumT    the thread's share of the forward PCHIP and trapezoid integrals of theta do
+//   allpos/allneg whether every interval of the thread steps up / down in theta
+// EDGE = false: every point j = -1..9 exists and none is an end of the profile (the bulk of a long
+// profile): no predicates, 16-byte loads when the chunk is aligned.  EDGE = true: the first and last
+// tiles of a profile and short profiles, every access guarded and the end formulas applied.
+template <bool EDGE, bool SORP>
+__device__ __forceinline__ void thread_chunk(const double* __restrict__ th_g, const double* __restrict__ o_g,
+                                             long long n, long long rb, bool aligned, double (&d)[INV_ITEMS + 1],
+                                             double (&I)[INV_ITEMS], double& sumF, double& sumT, bool& allpos,
+                                             bool& allneg) {
+  constexpr int NP = INV_ITEMS + 3;  // points j = -1 .. 9, index a = j + 1
+  constexpr int NI = INV_ITEMS + 2;  // intervals (j, j+1), j = -1 .. 8, index b = j + 1
+  double x[NP], y[NP];
+  const long long top = n - 1 - rb;  // memory index of j = 0
+  if (!EDGE) {
+    const double* pt = th_g + (top - (INV_ITEMS - 1));  // memory-ascending chunk: pt[k] is j = 7-k
+    const double* po = o_g + (top - (INV_ITEMS - 1));
+    if (aligned) {
+#pragma unroll
+      for (int k = 0; k < INV_ITEMS; k += 2) {
+        const double2 a = *reinterpret_cast<const double2*>(pt + k);
+        const double2 c = *reinterpret_cast<const double2*>(po + k);
+        x[INV_ITEMS - k] = a.x;
+        x[INV_ITEMS - 1 - k] = a.y;
+        y[INV_ITEMS - k] = c.x;
+        y[INV_ITEMS - 1 - k] = c.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < INV_ITEMS; k++) {
+        x[INV_ITEMS - k] = pt[k];
+        y[INV_ITEMS - k] = po[k];
+      }
+    }
+    x[0] = pt[INV_ITEMS];
+    y[0] = po[INV_ITEMS];
+    x[INV_ITEMS + 1] = pt[-1];
+    y[INV_ITEMS + 1] = po[-1];
+    x[INV_ITEMS + 2] = pt[-2];
+    y[INV_ITEMS + 2] = po[-2];
+  } else {
+#pragma unroll
+    for (int a = 0; a < NP; a++) {
+      const long long r = rb + a - 1;
+      const bool ok = r >= 0 && r < n;
+      x[a] = ok ? th_g[n - 1 - r] : 0.0;
+      y[a] = ok ? o_g[n - 1 - r] : 0.0;
+    }
+  }
+
+  // signed steps and the strict sign of each interval's secant
+  double hx[NI], ho[NI];
+  bool mpos[NI], mneg[NI], xpos[NI], xneg[NI];
+#pragma unroll
+  for (int b = 0; b < NI; b++) {
+    hx[b] = x[b + 1] - x[b];
+    ho[b] = y[b + 1] - y[b];
+    xpos[b] = hx[b] > 0.0;
+    xneg[b] = hx[b] < 0.0;
+    const bool opos = ho[b] > 0.0, oneg = ho[b] < 0.0;
+    mpos[b] = (xpos[b] && opos) || (xneg[b] && oneg);
+    mneg[b] = (xpos[b] && oneg) || (xneg[b] && opos);
+  }
+
+  // slopes at j = 0..8: intervals b = j (before) and b = j+1 (after)
+  double df[INV_ITEMS + 1];
+#pragma unroll
+  for (int j = 0; j <= INV_ITEMS; j++) {
+    const bool same = (mpos[j] && mpos[j + 1]) || (mneg[j] && mneg[j + 1]);
+    d[j] = pchip_interior_steps(hx[j], ho[j], hx[j + 1], ho[j + 1], same);
+    if (SORP) df[j] = pchip_interior_steps(ho[j], hx[j], ho[j + 1], hx[j + 1], same);
+    if (EDGE) {
+      const long long r = rb + j;
+      const bool live = r < n, has_left = r >= 1, has_right = r <= n - 2;
+      if (!live) {
+        d[j] = 0.0;
+        if (SORP) df[j] = 0.0;
+      } else if (!(has_left && has_right)) {
+        if (n == 2) {
+          d[j] = has_right ? ho[j + 1] / hx[j + 1] : ho[j] / hx[j];
+          if (SORP) df[j] = has_right ? hx[j + 1] / ho[j + 1] : hx[j] / ho[j];
+        } else if (has_right) {  // r == 0, one-sided: intervals (0,1) and (1,2)
+          const double x0 = th_g[n - 1], x1 = th_g[n - 2], x2 = th_g[n - 3];
+          const double y0 = o_g[n - 1], y1 = o_g[n - 2], y2 = o_g[n - 3];
+          const double a1 = x1 - x0, a2 = x2 - x1, c1 = y1 - y0, c2 = y2 - y1;
+          d[j] = pchip_edge(a1, a2, c1 / a1, c2 / a2);
+          if (SORP) df[j] = pchip_edge(c1, c2, a1 / c1, a2 / c2);
+        } else {  // r == n-1, one-sided, mirrored: intervals (n-2,n-1) and (n-3,n-2)
+          const double x0 = th_g[0], x1 = th_g[1], x2 = th_g[2];
+          const double y0 = o_g[0], y1 = o_g[1], y2 = o_g[2];
+          const double a1 = x0 - x1, a2 = x1 - x2, c1 = y0 - y1, c2 = y1 - y2;
+          d[j] = pchip_edge(a1, a2, c1 / a1, c2 / a2);
+          if (SORP) df[j] = pchip_edge(c1, c2, a1 / c1, a2 / c2);
+        }
+      }
+    }
+  }
+
+  // per-interval cubic-Hermite integrals, intervals j = 0..7 (b = j+1)
+  sumF = 0.0;
+  sumT = 0.0;
+  allpos = true;
+  allneg = true;
+#pragma unroll
+  for (int j = 0; j < INV_ITEMS; j++) {
+    const int b = j + 1;
+    const double h = hx[b];
+    double v = h * fma(0.5, y[b] + y[b + 1], (d[j] - d[j + 1]) * (h * (1.0 / 12.0)));
+    bool exists = true;
+    if (EDGE) exists = rb + j <= n - 2;
+    I[j] = exists ? v : 0.0;
+    if (exists) {
+      allpos = allpos && xpos[b];
+      allneg = allneg && xneg[b];
+    }
+    if (SORP) {
+      const double g = ho[b];
+      const double trap = g * (0.5 * (x[b] + x[b + 1]));
+      if (exists) {
+        sumT += trap;
+        sumF += fma((df[j] - df[j + 1]) * g, g * (1.0 / 12.0), trap);
+      }
+    }
+  }
+}
+
+template <bool SORP>
+__global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArgs A) {
+  // a tile's output is written one tile later (see below): its slopes and in-tile prefixes wait here
+  __shared__ double2 s_def[INV_ITEMS][INV_BLOCK];
+  __shared__ double s_wt[INV_NW];
+  __shared__ double s_warp[2][INV_NW];
   __shared__ double s_red[INV_NAGG];
   __shared__ unsigned long long s_ticket;
   __shared__ int s_bad;
@@ -157,7 +284,6 @@ __global__ void __launch_bounds__(INV_BLOCK, 8) inverse_scan_kernel(const InvArg
   const unsigned lane = tid & 31, wid = tid >> 5;
   const long long total_tiles = A.batch * A.ntiles;
   const long long n = A.npts;
-  const bool two = (n == 2);
 
   // The prefix of a tile needs the aggregates of every earlier tile of its profile, which other
   // CTAs are computing at the same moment: waiting for them right away left 45 % of the warp
@@ -165,8 +291,6 @@ __global__ void __launch_bounds__(INV_BLOCK, 8) inverse_scan_kernel(const InvArg
   // its NEXT tile, and only then resolves the previous tile's prefix and writes its output.
   // Aggregates are published before anything is waited for, so this cannot deadlock.
   long long pv_p = -1, pv_t = 0;  // the deferred tile
-  double pv_excl[INV_ITEMS] = {0.0, 0.0, 0.0, 0.0};
-  int pv_buf = 0, buf = 0;
 
   for (;;) {
     __syncthreads();
@@ -179,150 +303,69 @@ __global__ void __launch_bounds__(INV_BLOCK, 8) inverse_scan_kernel(const InvArg
     const bool have = ticket < total_tiles;
     if (!have && pv_p < 0) break;
     long long p = 0, t = 0;
-    double excl[INV_ITEMS] = {0.0, 0.0, 0.0, 0.0};
+    double d[INV_ITEMS + 1], excl[INV_ITEMS];
 
     if (have) {
       p = ticket / A.ntiles;
       t = ticket - p * A.ntiles;
       const long long r0 = t * INV_TILE;
+      const long long rb = r0 + (long long)tid * INV_ITEMS;
       const double* th_g = A.theta + p * n;
       const double* o_g = A.o + p * n;
-      double* sd = s_d[buf];
-      const double dir_step = th_g[n - 2] - th_g[n - 1];  // issued early: needed after the slopes
+      const double dir_step = th_g[n - 2] - th_g[n - 1];  // direction of the profile, from interval r = 0
 
-      // ---- load tile + halo in traversal order (r -> caller index n-1-r) ----
-      // s[q] holds traversal point r0 - 2 + q, i.e. memory index jtop - q with jtop = n+1-r0
-      {
-        const double* th_top = th_g + (n + 1 - r0);
-        const double* o_top = o_g + (n + 1 - r0);
-        if (r0 >= INV_HALO_L && r0 + INV_TILE + 2 <= n) {  // every point of tile and halo exists
-          for (int q = tid; q < NS; q += INV_BLOCK) {
-            s_th[q] = th_top[-q];
-            s_o[q] = o_top[-q];
-          }
-        } else {
-          const long long qlo = INV_HALO_L - r0, qhi = n + INV_HALO_L - r0;  // valid q in [qlo, qhi)
-          for (int q = tid; q < NS; q += INV_BLOCK) {
-            const bool ok = q >= qlo && q < qhi;
-            s_th[q] = ok ? th_top[-q] : 0.0;
-            s_o[q] = ok ? o_top[-q] : 0.0;
-          }
-        }
+      double I[INV_ITEMS], sumF, sumT;
+      bool allpos, allneg;
+      // bulk tile: point r0-1 and the points up to r0+TILE+1 exist and r0+TILE is not the last one
+      if (r0 > 0 && r0 + INV_TILE + 2 <= n) {
+        const long long lo = n - INV_ITEMS - rb;  // first memory index of the thread's chunk
+        const bool aligned = (((uintptr_t)(th_g + lo) | (uintptr_t)(o_g + lo)) & 15) == 0;
+        thread_chunk<false, SORP>(th_g, o_g, n, rb, aligned, d, I, sumF, sumT, allpos, allneg);
+      } else {
+        thread_chunk<true, SORP>(th_g, o_g, n, rb, false, d, I, sumF, sumT, allpos, allneg);
       }
-      __syncthreads();
+      const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);
+      const bool bad = flat || !(up ? allpos : allneg);
 
-      // ---- slopes do/dtheta (inverse interpolant) and dtheta/do (forward) at r in [r0, r0+TILE] --
-      // Each lane forms the secants of the interval to the RIGHT of its point; the interval to the
-      // left is the previous lane's (one shuffle; lane 0 of a warp recomputes it).
-      const long long left = n - r0;                      // points of the profile from r0 on
-      const int npt = left > INV_TILE + 1 ? INV_TILE + 1 : (int)left;  // points e in [0, npt) exist
-      const bool first_tile = (r0 == 0);
-      const bool ends_here = left <= INV_TILE + 1;        // the profile's last point is e = npt-1
-      auto slope_at = [&](int e, bool shuffled) {
-        const int q = e + INV_HALO_L;
-        const bool live = e < npt;
-        const bool has_right = live && !(ends_here && e == npt - 1);
-        double hx1 = 0.0, ho1 = 0.0, m1 = 0.0, mf1 = 0.0;  // interval (q, q+1)
-        if (has_right) {
-          hx1 = s_th[q + 1] - s_th[q];
-          ho1 = s_o[q + 1] - s_o[q];
-          m1 = ho1 * rcp_lean(hx1);
-          mf1 = hx1 * rcp_lean(ho1);
-        }
-        double hx0, ho0, m0, mf0;
-        if (shuffled) {
-          hx0 = __shfl_up_sync(0xffffffffu, hx1, 1);
-          ho0 = __shfl_up_sync(0xffffffffu, ho1, 1);
-          m0 = __shfl_up_sync(0xffffffffu, m1, 1);
-          mf0 = __shfl_up_sync(0xffffffffu, mf1, 1);
-        }
-        const bool has_left = live && !(first_tile && e == 0);
-        if ((!shuffled || lane == 0) && has_left) {  // interval (q-1, q)
-          hx0 = s_th[q] - s_th[q - 1];
-          ho0 = s_o[q] - s_o[q - 1];
-          m0 = ho0 * rcp_lean(hx0);
-          mf0 = hx0 * rcp_lean(ho0);
-        }
-        if (live) {
-          double d, df;
-          if (has_left && has_right) {
-            d = pchip_interior_r(hx0, hx1, m0, m1, mf0, mf1);
-            df = pchip_interior_r(ho0, ho1, mf0, mf1, m0, m1);
-          } else if (two) {
-            d = has_right ? m1 : m0;
-            df = has_right ? mf1 : mf0;
-          } else if (has_right) {  // r == 0, one-sided: intervals (q, q+1) and (q+1, q+2)
-            double hx2 = s_th[q + 2] - s_th[q + 1], ho2 = s_o[q + 2] - s_o[q + 1];
-            d = pchip_edge(hx1, hx2, m1, ho2 / hx2);
-            df = pchip_edge(ho1, ho2, mf1, hx2 / ho2);
-          } else {  // r == n-1, one-sided, mirrored: intervals (q-1, q) and (q-2, q-1)
-            double hxm = s_th[q - 1] - s_th[q - 2], hom = s_o[q - 1] - s_o[q - 2];
-            d = pchip_edge(hx0, hxm, m0, hom / hxm);
-            df = pchip_edge(ho0, hom, mf0, hxm / hom);
-          }
-          sd[e] = d;
-          s_df[e] = df;
-        } else {
-          sd[e] = 0.0;
-          s_df[e] = 0.0;
-        }
-      };
+      // in-thread running sums, then one warp scan of the thread totals
+      double run = 0.0;
 #pragma unroll
-      for (int it = 0; it < INV_ITEMS; it++) slope_at(it * INV_BLOCK + tid, true);
-      if (tid == 0) slope_at(INV_TILE, false);  // the point that closes the tile's last interval
-      __syncthreads();
-
-      // ---- per-interval integrals and the block scan (one barrier) -----------------
-      double incl[INV_ITEMS], mine[INV_ITEMS];
-      double sumF = 0.0, sumT = 0.0;
-      int bad = 0;
-      const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);  // profile direction, from interval r=0
-#pragma unroll
-      for (int it = 0; it < INV_ITEMS; it++) {
-        int e = it * INV_BLOCK + tid;
-        long long r = r0 + e;
-        double I = 0.0;
-        if (r < n - 1) {
-          int q = e + INV_HALO_L;
-          double hx = s_th[q + 1] - s_th[q];  // signed step in theta
-          double ho = s_o[q + 1] - s_o[q];    // signed step in o
-          if (flat || !(up ? hx > 0.0 : hx < 0.0)) bad = 1;
-          double trap = ho * (s_th[q] + s_th[q + 1]) * 0.5;
-          I = hx * (s_o[q] + s_o[q + 1]) * 0.5 + hx * hx * (sd[e] - sd[e + 1]) * (1.0 / 12.0);
-          sumF += trap + ho * ho * (s_df[e] - s_df[e + 1]) * (1.0 / 12.0);
-          sumT += trap;
-        }
-        mine[it] = I;
-        incl[it] = warp_incl_scan(I, lane);
-        if (lane == 31) s_scan[it][wid] = incl[it];
+      for (int j = 0; j < INV_ITEMS; j++) {
+        excl[j] = run;
+        run += I[j];
       }
-      sumF = warp_sum(sumF);  // the two sorptivity integrands (fixed tree)
-      sumT = warp_sum(sumT);
-      if (lane == 0) {
-        s_warp[0][wid] = sumF;
-        s_warp[1][wid] = sumT;
+      const double wincl = warp_incl_scan(run, lane);
+      if (lane == 31) s_wt[wid] = wincl;
+      if (SORP) {
+        sumF = warp_sum(sumF);  // the two sorptivity integrands (fixed tree)
+        sumT = warp_sum(sumT);
+        if (lane == 0) {
+          s_warp[0][wid] = sumF;
+          s_warp[1][wid] = sumT;
+        }
       }
       if (bad) atomicOr(&s_bad, 1);
       __syncthreads();
-      // exclusive offsets of the ITEMS x 8 warp totals (item-major = traversal order): one warp scans them
-      if (wid == 0) {
-        const double v = ((int)lane < NWT) ? (&s_scan[0][0])[lane] : 0.0;
-        const double inc = warp_incl_scan(v, lane);
-        if ((int)lane < NWT) s_off[lane] = inc - v;
-        if (lane == 31) s_off[NWT] = inc;
-      }
-      __syncthreads();
-      const double carry = s_off[NWT];
+      double woff = 0.0, carry = 0.0;  // fixed order: bit-reproducible
 #pragma unroll
-      for (int it = 0; it < INV_ITEMS; it++) excl[it] = s_off[it * (INV_BLOCK / 32) + wid] + (incl[it] - mine[it]);
+      for (int w = 0; w < INV_NW; w++) {
+        const double v = s_wt[w];
+        if (w < (int)wid) woff += v;
+        carry += v;
+      }
+      const double toff = woff + (wincl - run);
+#pragma unroll
+      for (int j = 0; j < INV_ITEMS; j++) excl[j] += toff;
 
       // ---- publish the tile aggregate; close the group if this is its last tile to arrive ------
       if (wid == 0) {
         if (lane == 0) {
           double f = 0.0, z = 0.0;
-          for (int w = 0; w < INV_BLOCK / 32; w++) {
-            f += s_warp[0][w];
-            z += s_warp[1][w];
+          if (SORP) {
+            for (int w = 0; w < INV_NW; w++) {
+              f += s_warp[0][w];
+              z += s_warp[1][w];
+            }
           }
           double* ag = A.agg + (p * A.ntiles + t) * INV_NAGG;
           __stcg(ag + 0, carry);
@@ -382,23 +425,37 @@ __global__ void __launch_bounds__(INV_BLOCK, 8) inverse_scan_kernel(const InvArg
       }
       __syncthreads();
       const double prefix = s_red[0];
-      const long long r0 = t2 * INV_TILE;
-      const double* sd = s_d[pv_buf];
+      const long long rb2 = t2 * INV_TILE + (long long)tid * INV_ITEMS;
 
-      // D at the tile's points, caller order: traversal point r0 + e is memory index top - e
-      const long long top = p2 * n + (n - 1 - r0);
-      const long long left = n - r0;
-      const int npt = left > INV_TILE ? INV_TILE : (int)left;
-      double* D_top = A.D + top;
+      // D at the thread's points in the caller's order: traversal point rb2 + j is memory index lo + 7 - j
+      const long long lo = p2 * n + (n - INV_ITEMS - rb2);
+      double Dv[INV_ITEMS], Iv[INV_ITEMS], dv[INV_ITEMS];
 #pragma unroll
-      for (int it = 0; it < INV_ITEMS; it++) {
-        const int e = it * INV_BLOCK + tid;
-        if (e < npt) {
-          const double Iod = prefix + pv_excl[it];
-          D_top[-e] = -(sd[e] * Iod) * 0.5;
-          if (A.slope) A.slope[top - e] = sd[e];
-          if (A.anti) A.anti[top - e] = Iod;
-        }
+      for (int j = 0; j < INV_ITEMS; j++) {
+        const double2 de = s_def[j][tid];
+        dv[j] = de.x;
+        Iv[j] = prefix + de.y;
+        Dv[j] = -(de.x * Iv[j]) * 0.5;
+      }
+      const bool whole = rb2 + INV_ITEMS <= n;
+      if (whole && (((uintptr_t)(A.D + lo)) & 15) == 0) {
+#pragma unroll
+        for (int k = 0; k < INV_ITEMS; k += 2)
+          *reinterpret_cast<double2*>(A.D + lo + k) = make_double2(Dv[INV_ITEMS - 1 - k], Dv[INV_ITEMS - 2 - k]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < INV_ITEMS; j++)
+          if (rb2 + j < n) A.D[lo + (INV_ITEMS - 1 - j)] = Dv[j];
+      }
+      if (A.slope) {
+#pragma unroll
+        for (int j = 0; j < INV_ITEMS; j++)
+          if (rb2 + j < n) A.slope[lo + (INV_ITEMS - 1 - j)] = dv[j];
+      }
+      if (A.anti) {
+#pragma unroll
+        for (int j = 0; j < INV_ITEMS; j++)
+          if (rb2 + j < n) A.anti[lo + (INV_ITEMS - 1 - j)] = Iv[j];
       }
 
       // the last tile of a profile closes its sorptivity sums and status
@@ -406,45 +463,46 @@ __global__ void __launch_bounds__(INV_BLOCK, 8) inverse_scan_kernel(const InvArg
         const double* th_g = A.theta + p2 * n;
         const double* o_g = A.o + p2 * n;
         const double* own = A.agg + (p2 * A.ntiles + t2) * INV_NAGG;
-        double F = s_red[1] + __ldcg(own + 1), Z = s_red[2] + __ldcg(own + 2), nbad = s_red[3] + __ldcg(own + 3);
-        // traversal runs from o_last down to o_first: Int_{o_first}^{o_last} theta do = -sum
-        double* out = A.sorp + p2 * 4;
-        out[0] = -F;
-        out[1] = -Z;
-        // extrapolation of the first forward cubic from o_first back to 0 (scipy extrapolate=True)
-        double ext = 0.0;
-        double o0 = o_g[0];
-        if (o0 != 0.0 && n >= 2) {
-          double o1 = o_g[1], y0 = th_g[0], y1 = th_g[1];
-          double hh = o1 - o0, m = (y1 - y0) / hh;
-          double d0, d1;
-          if (n == 2) {
-            d0 = d1 = m;
-          } else {
-            double o2 = o_g[2], y2 = th_g[2];
-            double h1 = o2 - o1, m1 = (y2 - y1) / h1;
-            d0 = pchip_edge(hh, h1, m, m1);
-            d1 = (n == 3) ? pchip_edge(h1, hh, m1, m) : pchip_interior(hh, h1, m, m1);
-          }
-          double tt = (d0 + d1 - 2.0 * m) / hh;
-          double c0 = tt / hh, c1 = (m - d0) / hh - tt, c2 = d0, c3 = y0;
-          double u = 0.0 - o0;  // antiderivative at o=0 relative to o0
-          double anti = (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + c2 * 0.5) * u + c3) * u;
-          ext = -anti;  // Int_0^{o0}
-        }
-        out[2] = ext;
-        out[3] = 0.0;
+        const double nbad = s_red[3] + __ldcg(own + 3);
         A.status[p2] = (nbad != 0.0) ? 1 : 0;
+        if (SORP) {
+          double F = s_red[1] + __ldcg(own + 1), Z = s_red[2] + __ldcg(own + 2);
+          // traversal runs from o_last down to o_first: Int_{o_first}^{o_last} theta do = -sum
+          double* out = A.sorp + p2 * 4;
+          out[0] = -F;
+          out[1] = -Z;
+          // extrapolation of the first forward cubic from o_first back to 0 (scipy extrapolate=True)
+          double ext = 0.0;
+          double o0 = o_g[0];
+          if (o0 != 0.0 && n >= 2) {
+            double o1 = o_g[1], y0 = th_g[0], y1 = th_g[1];
+            double hh = o1 - o0, m = (y1 - y0) / hh;
+            double d0, d1;
+            if (n == 2) {
+              d0 = d1 = m;
+            } else {
+              double o2 = o_g[2], y2 = th_g[2];
+              double h1 = o2 - o1, m1 = (y2 - y1) / h1;
+              d0 = pchip_edge(hh, h1, m, m1);
+              d1 = (n == 3) ? pchip_edge(h1, hh, m1, m) : pchip_interior(hh, h1, m, m1);
+            }
+            double tt = (d0 + d1 - 2.0 * m) / hh;
+            double c0 = tt / hh, c1 = (m - d0) / hh - tt, c2 = d0, c3 = y0;
+            double u = 0.0 - o0;  // antiderivative at o=0 relative to o0
+            double anti = (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + c2 * 0.5) * u + c3) * u;
+            ext = -anti;  // Int_0^{o0}
+          }
+          out[2] = ext;
+          out[3] = 0.0;
+        }
       }
     }
 
     if (have) {
+#pragma unroll
+      for (int j = 0; j < INV_ITEMS; j++) s_def[j][tid] = make_double2(d[j], excl[j]);
       pv_p = p;
       pv_t = t;
-#pragma unroll
-      for (int it = 0; it < INV_ITEMS; it++) pv_excl[it] = excl[it];
-      pv_buf = buf;
-      buf ^= 1;
     } else {
       pv_p = -1;
     }
@@ -574,13 +632,15 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   e = cudaMemsetAsync(scratch + agg_bytes, 0, cnt_bytes + 64, s);
   if (e != cudaSuccess) return e;
   int bps = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, inverse_scan_kernel, INV_BLOCK, 0);
+  e = sorp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, inverse_scan_kernel<true>, INV_BLOCK, 0)
+           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, inverse_scan_kernel<false>, INV_BLOCK, 0);
   if (e != cudaSuccess) return e;
   if (bps < 1) bps = 1;
   long long cap = (long long)sms * bps;
   int grid = (int)((long long)tiles < cap ? (long long)tiles : cap);
   if (grid < 1) grid = 1;
-  inverse_scan_kernel<<<grid, INV_BLOCK, 0, s>>>(a);
+  if (sorp) inverse_scan_kernel<true><<<grid, INV_BLOCK, 0, s>>>(a);
+  else inverse_scan_kernel<false><<<grid, INV_BLOCK, 0, s>>>(a);
   *launches = 1;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
