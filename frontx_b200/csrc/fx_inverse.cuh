@@ -140,65 +140,88 @@ __device__ __forceinline__ void wait_load4(const double* src, double (&v)[4]) {
   }
 }
 
-// What one thread makes of its INV_ITEMS consecutive points, all in registers.  Traversal point
-// j = 0..7 of the thread is profile traversal index rb + j, memory index n-1-rb-j.
-//   d[j], df[j]   do/dtheta and dtheta/do at point j = 0..8 (8 closes the thread's last interval)
+__device__ __forceinline__ double wait_load1(const double* src) {
+  double v;
+  for (;;) {
+    v = __ldcg(src);
+    if (!is_unset(v)) break;
+    __nanosleep(20);
+  }
+  return v;
+}
+
+constexpr int INV_NP = INV_ITEMS + 3;  // points j = -1 .. 9 held by a thread, index a = j + 1
+constexpr int INV_NI = INV_ITEMS + 2;  // intervals (j, j+1), j = -1 .. 8, index b = j + 1
+
+// cp.async: global -> shared without passing through registers, so a tile's points can be requested
+// a whole tile ahead at no register cost.  Every thread stages ITS OWN points in ITS OWN slots and is
+// the only reader of them: cp.async.wait_all orders the copy for the issuing thread, no barrier.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src, bool ok) {  // !ok: zero-fill, nothing read
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int bytes = ok ? 8 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int INV_SLOTS = (INV_NP + 1) / 2;  // 16-byte slots holding a thread's 11 points of one array
+
+// Request the points one thread works on.  Traversal point j = 0..7 of the thread is profile
+// traversal index rb + j, memory index n-1-rb-j; j = -1, 8, 9 are the halo its slopes need.  They are
+// staged in memory order: element e = 0..10 is memory index (n-10-rb) + e, i.e. j = 9 - e.
+// EDGE = false: every one of them exists (the bulk of a long profile); A16: the chunk is 16-byte
+// aligned (even npts, aligned arrays).  EDGE = true: first/last tiles and short profiles, guarded.
+template <bool EDGE, bool A16>
+__device__ __forceinline__ void request_chunk(const double* __restrict__ g, long long n, long long rb,
+                                              double2 (*slot)[INV_BLOCK], int tid) {
+  const double* base = g + (n - INV_ITEMS - 2 - rb);  // element 0
+  if (!EDGE && A16) {
+#pragma unroll
+    for (int q = 0; q < INV_SLOTS - 1; q++) cp_async16(&slot[q][tid], base + 2 * q);
+    cp_async8(&slot[INV_SLOTS - 1][tid].x, base + 2 * (INV_SLOTS - 1), true);
+  } else {
+#pragma unroll
+    for (int e = 0; e < INV_NP; e++) {
+      bool ok = true;
+      if (EDGE) {
+        const long long r = rb + (INV_ITEMS + 1 - e);
+        ok = r >= 0 && r < n;
+      }
+      double* dst = reinterpret_cast<double*>(&slot[e >> 1][tid]) + (e & 1);
+      cp_async8(dst, ok ? base + e : g, ok);
+    }
+  }
+}
+// ... and pick them up: x[a] is point j = a - 1, element e = 10 - a
+__device__ __forceinline__ void collect_chunk(const double2 (*slot)[INV_BLOCK], int tid, double (&x)[INV_NP]) {
+#pragma unroll
+  for (int q = 0; q < INV_SLOTS; q++) {
+    const double2 v = slot[q][tid];
+    x[INV_NP - 1 - 2 * q] = v.x;
+    if (2 * q + 1 < INV_NP) x[INV_NP - 2 - 2 * q] = v.y;
+  }
+}
+
+// What one thread makes of its points:
+//   d[j]          do/dtheta at point j = 0..8 (8 closes the thread's last interval)
 //   I[j]          Int o dtheta over the interval (j, j+1), j = 0..7
 //   sumF, sumT    the thread's share of the forward PCHIP and trapezoid integrals of theta do
 //   allpos/allneg whether every interval of the thread steps up / down in theta
-// EDGE = false: every point j = -1..9 exists and none is an end of the profile (the bulk of a long
-// profile): no predicates, 16-byte loads when the chunk is aligned.  EDGE = true: the first and last
-// tiles of a profile and short profiles, every access guarded and the end formulas applied.
+// EDGE = true applies the end-point formulas and drops what lies beyond the profile.
 template <bool EDGE, bool SORP>
-__device__ __forceinline__ void thread_chunk(const double* __restrict__ th_g, const double* __restrict__ o_g,
-                                             long long n, long long rb, bool aligned, double (&d)[INV_ITEMS + 1],
-                                             double (&I)[INV_ITEMS], double& sumF, double& sumT, bool& allpos,
-                                             bool& allneg) {
-  constexpr int NP = INV_ITEMS + 3;  // points j = -1 .. 9, index a = j + 1
-  constexpr int NI = INV_ITEMS + 2;  // intervals (j, j+1), j = -1 .. 8, index b = j + 1
-  double x[NP], y[NP];
-  const long long top = n - 1 - rb;  // memory index of j = 0
-  if (!EDGE) {
-    const double* pt = th_g + (top - (INV_ITEMS - 1));  // memory-ascending chunk: pt[k] is j = 7-k
-    const double* po = o_g + (top - (INV_ITEMS - 1));
-    if (aligned) {
-#pragma unroll
-      for (int k = 0; k < INV_ITEMS; k += 2) {
-        const double2 a = *reinterpret_cast<const double2*>(pt + k);
-        const double2 c = *reinterpret_cast<const double2*>(po + k);
-        x[INV_ITEMS - k] = a.x;
-        x[INV_ITEMS - 1 - k] = a.y;
-        y[INV_ITEMS - k] = c.x;
-        y[INV_ITEMS - 1 - k] = c.y;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < INV_ITEMS; k++) {
-        x[INV_ITEMS - k] = pt[k];
-        y[INV_ITEMS - k] = po[k];
-      }
-    }
-    x[0] = pt[INV_ITEMS];
-    y[0] = po[INV_ITEMS];
-    x[INV_ITEMS + 1] = pt[-1];
-    y[INV_ITEMS + 1] = po[-1];
-    x[INV_ITEMS + 2] = pt[-2];
-    y[INV_ITEMS + 2] = po[-2];
-  } else {
-#pragma unroll
-    for (int a = 0; a < NP; a++) {
-      const long long r = rb + a - 1;
-      const bool ok = r >= 0 && r < n;
-      x[a] = ok ? th_g[n - 1 - r] : 0.0;
-      y[a] = ok ? o_g[n - 1 - r] : 0.0;
-    }
-  }
-
+__device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, const double* __restrict__ o_g,
+                                              long long n, long long rb, const double (&x)[INV_NP],
+                                              const double (&y)[INV_NP], double (&d)[INV_ITEMS + 1],
+                                              double (&I)[INV_ITEMS], double& sumF, double& sumT, bool& allpos,
+                                              bool& allneg) {
   // signed steps and the strict sign of each interval's secant
-  double hx[NI], ho[NI];
-  bool mpos[NI], mneg[NI], xpos[NI], xneg[NI];
+  double hx[INV_NI], ho[INV_NI];
+  bool mpos[INV_NI], mneg[INV_NI], xpos[INV_NI], xneg[INV_NI];
 #pragma unroll
-  for (int b = 0; b < NI; b++) {
+  for (int b = 0; b < INV_NI; b++) {
     hx[b] = x[b + 1] - x[b];
     ho[b] = y[b + 1] - y[b];
     xpos[b] = hx[b] > 0.0;
@@ -270,15 +293,42 @@ __device__ __forceinline__ void thread_chunk(const double* __restrict__ th_g, co
   }
 }
 
-template <bool SORP>
+// Sum over the tiles before tile t of profile p of the first NC components of their aggregates, by
+// one warp, every lane returning the same value.  Two fixed levels, no chain: whoever publishes the
+// last aggregate of a group of INV_GROUP tiles also publishes the group total; a tile adds the totals
+// of all earlier groups and the aggregates of its own group's earlier tiles.
+// O(ntiles/INV_GROUP + INV_GROUP) reads and -- the association being fixed by the tile index
+// alone -- bit-reproducible run to run, and the same in every warp that asks.
+template <int NC>
+__device__ __forceinline__ void look_back(const InvArgs& A, long long p, long long t, unsigned lane,
+                                          double (&part)[NC]) {
+  const long long g = t / INV_GROUP, g0 = g * INV_GROUP;
+#pragma unroll
+  for (int c = 0; c < NC; c++) part[c] = 0.0;
+  for (long long gi = lane; gi < g; gi += 32) {
+    const double* src = A.gtot + (p * A.ngroups + gi) * INV_NAGG;
+#pragma unroll
+    for (int c = 0; c < NC; c++) part[c] += wait_load1(src + c);
+  }
+  const long long k = g0 + lane;
+  if (k < t) {
+    const double* src = A.agg + (p * A.ntiles + k) * INV_NAGG;
+#pragma unroll
+    for (int c = 0; c < NC; c++) part[c] += wait_load1(src + c);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) part[c] = warp_sum(part[c]);
+}
+
+template <bool SORP, bool A16>
 __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArgs A) {
-  // a tile's output is written one tile later (see below): its slopes and in-tile prefixes wait here
+  __shared__ double2 s_in[2][INV_SLOTS][INV_BLOCK];  // the next tile's (theta, o), each thread's own points
+  // A tile's output is written one tile later (see below): its slopes and in-tile prefixes wait here,
+  // each thread's in its own slots.
   __shared__ double2 s_def[INV_ITEMS][INV_BLOCK];
-  __shared__ double s_wt[INV_NW];
-  __shared__ double s_warp[2][INV_NW];
-  __shared__ double s_red[INV_NAGG];
-  __shared__ unsigned long long s_ticket;
-  __shared__ int s_bad;
+  __shared__ double s_wt[2][INV_NW];
+  __shared__ double s_warp[2][2][INV_NW];
+  __shared__ unsigned long long s_tick[2];
 
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
@@ -287,69 +337,94 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
 
   // The prefix of a tile needs the aggregates of every earlier tile of its profile, which other
   // CTAs are computing at the same moment: waiting for them right away left 45 % of the warp
-  // time at that barrier.  So a tile publishes its aggregate, the CTA goes on to load and scan
-  // its NEXT tile, and only then resolves the previous tile's prefix and writes its output.
-  // Aggregates are published before anything is waited for, so this cannot deadlock.
+  // time there.  So a tile publishes its aggregate, the CTA requests the points of its NEXT tile
+  // (cp.async), and only then each warp resolves the previous tile's prefix and writes its output.
+  // Tickets are taken one tile ahead (so the requests can be) and in order; aggregates are published
+  // before anything is waited for and a blocked CTA only ever holds unpublished tiles LATER than
+  // the one it waits on, so the waits cannot form a cycle.
+  auto bulk_tile = [&](long long t) {  // point r0-1 and the points up to r0+TILE+1 exist, r0+TILE is not the last
+    const long long r0 = t * INV_TILE;
+    return r0 > 0 && r0 + INV_TILE + 2 <= n;
+  };
+
+  if (tid == 0) s_tick[0] = atomicAdd(A.ticket, 1ull);
+  __syncthreads();
+  long long ticket = (long long)s_tick[0];
+  bool have = ticket < total_tiles;
+  long long p = 0, t = 0;
+  auto request_tile = [&]() {
+    p = ticket / A.ntiles;
+    t = ticket - p * A.ntiles;
+    const long long rb = t * INV_TILE + (long long)tid * INV_ITEMS;
+    const double* th_g = A.theta + p * n;
+    const double* o_g = A.o + p * n;
+    if (bulk_tile(t)) {
+      request_chunk<false, A16>(th_g, n, rb, s_in[0], tid);
+      request_chunk<false, A16>(o_g, n, rb, s_in[1], tid);
+    } else {
+      request_chunk<true, false>(th_g, n, rb, s_in[0], tid);
+      request_chunk<true, false>(o_g, n, rb, s_in[1], tid);
+    }
+  };
+  if (have) request_tile();
+
   long long pv_p = -1, pv_t = 0;  // the deferred tile
+  int par = 0;
 
   for (;;) {
-    __syncthreads();
-    if (tid == 0) {
-      s_ticket = atomicAdd(A.ticket, 1ull);
-      s_bad = 0;
-    }
-    __syncthreads();
-    const long long ticket = (long long)s_ticket;
-    const bool have = ticket < total_tiles;
     if (!have && pv_p < 0) break;
-    long long p = 0, t = 0;
+    if (tid == 0 && have) s_tick[par ^ 1] = atomicAdd(A.ticket, 1ull);
     double d[INV_ITEMS + 1], excl[INV_ITEMS];
-
+    double run = 0.0, wincl = 0.0;
+    bool bad = false;
     if (have) {
-      p = ticket / A.ntiles;
-      t = ticket - p * A.ntiles;
-      const long long r0 = t * INV_TILE;
-      const long long rb = r0 + (long long)tid * INV_ITEMS;
+      const long long rb = t * INV_TILE + (long long)tid * INV_ITEMS;
       const double* th_g = A.theta + p * n;
       const double* o_g = A.o + p * n;
       const double dir_step = th_g[n - 2] - th_g[n - 1];  // direction of the profile, from interval r = 0
-
+      double x[INV_NP], y[INV_NP];
+      cp_async_wait_all();
+      collect_chunk(s_in[0], tid, x);
+      collect_chunk(s_in[1], tid, y);
       double I[INV_ITEMS], sumF, sumT;
       bool allpos, allneg;
-      // bulk tile: point r0-1 and the points up to r0+TILE+1 exist and r0+TILE is not the last one
-      if (r0 > 0 && r0 + INV_TILE + 2 <= n) {
-        const long long lo = n - INV_ITEMS - rb;  // first memory index of the thread's chunk
-        const bool aligned = (((uintptr_t)(th_g + lo) | (uintptr_t)(o_g + lo)) & 15) == 0;
-        thread_chunk<false, SORP>(th_g, o_g, n, rb, aligned, d, I, sumF, sumT, allpos, allneg);
-      } else {
-        thread_chunk<true, SORP>(th_g, o_g, n, rb, false, d, I, sumF, sumT, allpos, allneg);
-      }
+      if (bulk_tile(t)) compute_chunk<false, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, allpos, allneg);
+      else compute_chunk<true, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, allpos, allneg);
       const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);
-      const bool bad = flat || !(up ? allpos : allneg);
+      bad = flat || !(up ? allpos : allneg);
 
       // in-thread running sums, then one warp scan of the thread totals
-      double run = 0.0;
 #pragma unroll
       for (int j = 0; j < INV_ITEMS; j++) {
         excl[j] = run;
         run += I[j];
       }
-      const double wincl = warp_incl_scan(run, lane);
-      if (lane == 31) s_wt[wid] = wincl;
+      wincl = warp_incl_scan(run, lane);
+      if (lane == 31) s_wt[par][wid] = wincl;
       if (SORP) {
         sumF = warp_sum(sumF);  // the two sorptivity integrands (fixed tree)
         sumT = warp_sum(sumT);
         if (lane == 0) {
-          s_warp[0][wid] = sumF;
-          s_warp[1][wid] = sumT;
+          s_warp[par][0][wid] = sumF;
+          s_warp[par][1][wid] = sumT;
         }
       }
-      if (bad) atomicOr(&s_bad, 1);
-      __syncthreads();
+    }
+    const int anybad = __syncthreads_or(bad ? 1 : 0);  // the one barrier of a tile
+    const long long next_ticket = have ? (long long)s_tick[par ^ 1] : total_tiles;
+
+    // ---- the points of the next tile are requested before anything is waited for --------------------
+    const long long this_p = p, this_t = t;
+    const bool had = have;
+    ticket = next_ticket;
+    have = ticket < total_tiles;
+    if (have) request_tile();
+
+    if (had) {
       double woff = 0.0, carry = 0.0;  // fixed order: bit-reproducible
 #pragma unroll
       for (int w = 0; w < INV_NW; w++) {
-        const double v = s_wt[w];
+        const double v = s_wt[par][w];
         if (w < (int)wid) woff += v;
         carry += v;
       }
@@ -363,29 +438,29 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
           double f = 0.0, z = 0.0;
           if (SORP) {
             for (int w = 0; w < INV_NW; w++) {
-              f += s_warp[0][w];
-              z += s_warp[1][w];
+              f += s_warp[par][0][w];
+              z += s_warp[par][1][w];
             }
           }
-          double* ag = A.agg + (p * A.ntiles + t) * INV_NAGG;
+          double* ag = A.agg + (this_p * A.ntiles + this_t) * INV_NAGG;
           __stcg(ag + 0, carry);
           __stcg(ag + 1, f);
           __stcg(ag + 2, z);
-          __stcg(ag + 3, (double)s_bad);
+          __stcg(ag + 3, (double)anybad);
           __threadfence();  // ordered before the arrival count below
         }
-        const long long g = t / INV_GROUP, g0 = g * INV_GROUP;
+        const long long g = this_t / INV_GROUP, g0 = g * INV_GROUP;
         const bool full = g < A.ntiles / INV_GROUP;
         int arrived = 0;
-        if (lane == 0 && full) arrived = atomicAdd(A.gcount + p * A.ngroups + g, 1);
+        if (lane == 0 && full) arrived = atomicAdd(A.gcount + this_p * A.ngroups + g, 1);
         arrived = __shfl_sync(0xffffffffu, arrived, 0);
         if (full && arrived == INV_GROUP - 1) {
           double tot[INV_NAGG];
-          wait_load4(A.agg + (p * A.ntiles + g0 + lane) * INV_NAGG, tot);
+          wait_load4(A.agg + (this_p * A.ntiles + g0 + lane) * INV_NAGG, tot);
 #pragma unroll
           for (int c = 0; c < INV_NAGG; c++) tot[c] = warp_sum(tot[c]);
           if (lane == 0) {
-            double* gt = A.gtot + (p * A.ngroups + g) * INV_NAGG;
+            double* gt = A.gtot + (this_p * A.ngroups + g) * INV_NAGG;
 #pragma unroll
             for (int c = 0; c < INV_NAGG; c++) __stcg(gt + c, tot[c]);
           }
@@ -393,38 +468,19 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       }
     }
 
-    // ---- the deferred tile: prefix over the earlier tiles of its profile, then its output --------
-    // Two fixed levels, no chain: whoever publishes the last aggregate of a group of INV_GROUP
-    // tiles also publishes the group total (above); a tile adds the totals of all earlier groups
-    // and the aggregates of its own group's earlier tiles.  O(ntiles/INV_GROUP + INV_GROUP) reads
-    // and -- the association being fixed by the tile index alone -- bit-reproducible run to run.
+    // ---- the deferred tile: every warp sums the earlier tiles of its profile, then writes its output --
     if (pv_p >= 0) {
       const long long p2 = pv_p, t2 = pv_t;
-      if (wid == 0) {
-        const long long g = t2 / INV_GROUP, g0 = g * INV_GROUP;
-        double part[INV_NAGG] = {0.0, 0.0, 0.0, 0.0};
-        for (long long gi = lane; gi < g; gi += 32) {
-          double v[INV_NAGG];
-          wait_load4(A.gtot + (p2 * A.ngroups + gi) * INV_NAGG, v);
-#pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) part[c] += v[c];
-        }
-        const long long k = g0 + lane;
-        if (k < t2) {
-          double v[INV_NAGG];
-          wait_load4(A.agg + (p2 * A.ntiles + k) * INV_NAGG, v);
-#pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) part[c] += v[c];
-        }
-#pragma unroll
-        for (int c = 0; c < INV_NAGG; c++) part[c] = warp_sum(part[c]);
-        if (lane == 0) {
-#pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) s_red[c] = part[c];
-        }
+      const bool closes = (t2 == A.ntiles - 1) && wid == 0;  // the last tile of a profile closes its sums
+      double prefix, tot[INV_NAGG];
+      if (closes) {
+        look_back<INV_NAGG>(A, p2, t2, lane, tot);
+        prefix = tot[0];
+      } else {
+        double one[1];
+        look_back<1>(A, p2, t2, lane, one);
+        prefix = one[0];
       }
-      __syncthreads();
-      const double prefix = s_red[0];
       const long long rb2 = t2 * INV_TILE + (long long)tid * INV_ITEMS;
 
       // D at the thread's points in the caller's order: traversal point rb2 + j is memory index lo + 7 - j
@@ -437,8 +493,7 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
         Iv[j] = prefix + de.y;
         Dv[j] = -(de.x * Iv[j]) * 0.5;
       }
-      const bool whole = rb2 + INV_ITEMS <= n;
-      if (whole && (((uintptr_t)(A.D + lo)) & 15) == 0) {
+      if (A16 && rb2 + INV_ITEMS <= n) {
 #pragma unroll
         for (int k = 0; k < INV_ITEMS; k += 2)
           *reinterpret_cast<double2*>(A.D + lo + k) = make_double2(Dv[INV_ITEMS - 1 - k], Dv[INV_ITEMS - 2 - k]);
@@ -458,15 +513,14 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
           if (rb2 + j < n) A.anti[lo + (INV_ITEMS - 1 - j)] = Iv[j];
       }
 
-      // the last tile of a profile closes its sorptivity sums and status
-      if (t2 == A.ntiles - 1 && tid == 0) {
+      if (closes && lane == 0) {
         const double* th_g = A.theta + p2 * n;
         const double* o_g = A.o + p2 * n;
         const double* own = A.agg + (p2 * A.ntiles + t2) * INV_NAGG;
-        const double nbad = s_red[3] + __ldcg(own + 3);
+        const double nbad = tot[3] + __ldcg(own + 3);
         A.status[p2] = (nbad != 0.0) ? 1 : 0;
         if (SORP) {
-          double F = s_red[1] + __ldcg(own + 1), Z = s_red[2] + __ldcg(own + 2);
+          double F = tot[1] + __ldcg(own + 1), Z = tot[2] + __ldcg(own + 2);
           // traversal runs from o_last down to o_first: Int_{o_first}^{o_last} theta do = -sum
           double* out = A.sorp + p2 * 4;
           out[0] = -F;
@@ -498,14 +552,13 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       }
     }
 
-    if (have) {
+    if (had) {
 #pragma unroll
       for (int j = 0; j < INV_ITEMS; j++) s_def[j][tid] = make_double2(d[j], excl[j]);
-      pv_p = p;
-      pv_t = t;
-    } else {
-      pv_p = -1;
     }
+    pv_p = had ? this_p : -1;
+    pv_t = this_t;
+    par ^= 1;
   }
 }
 
@@ -631,16 +684,18 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(scratch + agg_bytes, 0, cnt_bytes + 64, s);
   if (e != cudaSuccess) return e;
+  // 16-byte loads and stores need every profile's chunks aligned: even npts and aligned arrays
+  const bool a16 = (npts % 2 == 0) && ((((uintptr_t)o | (uintptr_t)theta | (uintptr_t)D) & 15) == 0);
+  void (*kern)(const InvArgs) = sorp ? (a16 ? inverse_scan_kernel<true, true> : inverse_scan_kernel<true, false>)
+                                     : (a16 ? inverse_scan_kernel<false, true> : inverse_scan_kernel<false, false>);
   int bps = 1;
-  e = sorp ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, inverse_scan_kernel<true>, INV_BLOCK, 0)
-           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, inverse_scan_kernel<false>, INV_BLOCK, 0);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, INV_BLOCK, 0);
   if (e != cudaSuccess) return e;
   if (bps < 1) bps = 1;
   long long cap = (long long)sms * bps;
   int grid = (int)((long long)tiles < cap ? (long long)tiles : cap);
   if (grid < 1) grid = 1;
-  if (sorp) inverse_scan_kernel<true><<<grid, INV_BLOCK, 0, s>>>(a);
-  else inverse_scan_kernel<false><<<grid, INV_BLOCK, 0, s>>>(a);
+  kern<<<grid, INV_BLOCK, 0, s>>>(a);
   *launches = 1;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
