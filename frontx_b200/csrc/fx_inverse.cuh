@@ -248,10 +248,10 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, c
         if (n == 2) {
           d[j] = has_right ? ho[j + 1] / hx[j + 1] : ho[j] / hx[j];
           if (SORP) df[j] = has_right ? hx[j + 1] / ho[j + 1] : hx[j] / ho[j];
-        } else if (has_right) {  // r == 0, one-sided: intervals (0,1) and (1,2)
-          const double x0 = th_g[n - 1], x1 = th_g[n - 2], x2 = th_g[n - 3];
-          const double y0 = o_g[n - 1], y1 = o_g[n - 2], y2 = o_g[n - 3];
-          const double a1 = x1 - x0, a2 = x2 - x1, c1 = y1 - y0, c2 = y2 - y1;
+        } else if (has_right) {  // r == 0, one-sided: intervals (0,1) and (1,2), both staged (every later
+          // tile of the profile waits for this one: nothing here goes back to global memory)
+          const int b2 = j + 2 < INV_NI ? j + 2 : INV_NI - 1;  // r == 0 is the j = 0 of one thread
+          const double a1 = hx[j + 1], a2 = hx[b2], c1 = ho[j + 1], c2 = ho[b2];
           d[j] = pchip_edge(a1, a2, c1 / a1, c2 / a2);
           if (SORP) df[j] = pchip_edge(c1, c2, a1 / c1, a2 / c2);
         } else {  // r == n-1, one-sided, mirrored: intervals (n-2,n-1) and (n-3,n-2)
@@ -352,12 +352,15 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
   long long ticket = (long long)s_tick[0];
   bool have = ticket < total_tiles;
   long long p = 0, t = 0;
+  double dir_a = 0.0, dir_b = 0.0;  // the profile's first traversal step tells its direction
   auto request_tile = [&]() {
     p = ticket / A.ntiles;
     t = ticket - p * A.ntiles;
     const long long rb = t * INV_TILE + (long long)tid * INV_ITEMS;
     const double* th_g = A.theta + p * n;
     const double* o_g = A.o + p * n;
+    dir_a = th_g[n - 2];
+    dir_b = th_g[n - 1];
     if (bulk_tile(t)) {
       request_chunk<false, A16>(th_g, n, rb, s_in[0], tid);
       request_chunk<false, A16>(o_g, n, rb, s_in[1], tid);
@@ -381,7 +384,7 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       const long long rb = t * INV_TILE + (long long)tid * INV_ITEMS;
       const double* th_g = A.theta + p * n;
       const double* o_g = A.o + p * n;
-      const double dir_step = th_g[n - 2] - th_g[n - 1];  // direction of the profile, from interval r = 0
+      const double dir_step = dir_a - dir_b;
       double x[INV_NP], y[INV_NP];
       cp_async_wait_all();
       collect_chunk(s_in[0], tid, x);
@@ -447,8 +450,9 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
           __stcg(ag + 1, f);
           __stcg(ag + 2, z);
           __stcg(ag + 3, (double)anybad);
-          __threadfence();  // ordered before the arrival count below
         }
+        // the arrival count only elects who closes the group; the closer waits for the VALUES (wait_load4),
+        // so no fence is needed between the stores above and the count
         const long long g = this_t / INV_GROUP, g0 = g * INV_GROUP;
         const bool full = g < A.ntiles / INV_GROUP;
         int arrived = 0;
