@@ -302,19 +302,31 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, c
 template <int NC>
 __device__ __forceinline__ void look_back(const InvArgs& A, long long p, long long t, unsigned lane,
                                           double (&part)[NC]) {
-  const long long g = t / INV_GROUP, g0 = g * INV_GROUP;
+  const long long g = t / INV_GROUP, k = g * INV_GROUP + lane;
+  const double* sg = A.gtot + (p * A.ngroups + lane) * INV_NAGG;
+  const double* sa = A.agg + (p * A.ntiles + k) * INV_NAGG;
+  const bool need_g = (long long)lane < g, need_a = k < t;
+  // both levels requested at once: one L2 round trip when everything is there, as it usually is
+  double vg[NC], va[NC];
 #pragma unroll
-  for (int c = 0; c < NC; c++) part[c] = 0.0;
-  for (long long gi = lane; gi < g; gi += 32) {
+  for (int c = 0; c < NC; c++) {
+    vg[c] = need_g ? __ldcg(sg + c) : 0.0;
+    va[c] = need_a ? __ldcg(sa + c) : 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    if (is_unset(vg[c])) vg[c] = wait_load1(sg + c);
+    part[c] = vg[c];
+  }
+  for (long long gi = lane + 32; gi < g; gi += 32) {  // profiles beyond 32 groups (33 M points)
     const double* src = A.gtot + (p * A.ngroups + gi) * INV_NAGG;
 #pragma unroll
     for (int c = 0; c < NC; c++) part[c] += wait_load1(src + c);
   }
-  const long long k = g0 + lane;
-  if (k < t) {
-    const double* src = A.agg + (p * A.ntiles + k) * INV_NAGG;
 #pragma unroll
-    for (int c = 0; c < NC; c++) part[c] += wait_load1(src + c);
+  for (int c = 0; c < NC; c++) {
+    if (is_unset(va[c])) va[c] = wait_load1(sa + c);
+    part[c] += va[c];
   }
 #pragma unroll
   for (int c = 0; c < NC; c++) part[c] = warp_sum(part[c]);

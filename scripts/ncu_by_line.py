@@ -69,3 +69,10 @@ for (a, loc, txt), p in zip(seq, prof):
 print()
 print("opcode mix (% of warp instructions):")
 print(", ".join(f"{k} {v / tot * 100:.1f}" for k, v in sorted(op.items(), key=lambda x: -x[1])[:28]))
+
+if len(sys.argv) > 5:  # top SASS instructions by samples
+    print("\ntop SASS instructions by samples:")
+    order = sorted(range(len(seq)), key=lambda k: -prof[k][3])[: int(sys.argv[5])]
+    for k in order:
+        a, loc, txt = seq[k]
+        print(f"{a:6x} {str(loc):28s} samples {prof[k][3] / tots * 100:5.2f}% exec {prof[k][1]:12.0f} thr/inst {prof[k][2] / max(prof[k][1], 1):5.1f}  {txt}")
