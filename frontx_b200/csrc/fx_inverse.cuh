@@ -154,11 +154,10 @@ constexpr int INV_NP = INV_ITEMS + 3;  // points j = -1 .. 9 held by a thread, i
 constexpr int INV_NI = INV_ITEMS + 2;  // intervals (j, j+1), j = -1 .. 8, index b = j + 1
 
 // cp.async: global -> shared without passing through registers, so a tile's points can be requested
-// a whole tile ahead at no register cost.  Every thread stages ITS OWN points in ITS OWN slots and is
-// the only reader of them: cp.async.wait_all orders the copy for the issuing thread, no barrier.
+// a whole tile ahead at no register cost.
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async8(void* dst, const void* src, bool ok) {  // !ok: zero-fill, nothing read
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -167,42 +166,64 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src, bool ok) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-constexpr int INV_SLOTS = (INV_NP + 1) / 2;  // 16-byte slots holding a thread's 11 points of one array
+// A WARP owns 32 * INV_ITEMS = 256 consecutive points of the tile and stages them itself, as 16-byte
+// chunks of two points: lane l copies chunk 32 q + l, so one instruction moves 512 contiguous bytes
+// (whole sectors, no reliance on L1), and thread u (in memory order, u = 31 - lane) then reads ITS
+// chunks 4u-1 .. 4u+4.  The chunk position is swizzled within its 128-byte row so that both the
+// copy and the 16-byte reads at a 64-byte stride are free of bank conflicts.  Only the warp reads
+// what it staged: cp.async.wait_all + __syncwarp, no CTA barrier.
+static_assert(INV_ITEMS == 8, "the chunk swizzle is laid out for four chunks per thread");
+constexpr int INV_CH = INV_ITEMS / 2;      // chunks per thread
+constexpr int INV_WCH = 32 * INV_CH;       // chunks per warp; two more hold the halo either side
+constexpr int INV_WPTS = 32 * INV_ITEMS;   // points per warp
+__device__ __forceinline__ int swz(int c) { return (c & ~7) | ((c & 7) ^ ((c >> 3) & 3)); }
 
-// Request the points one thread works on.  Traversal point j = 0..7 of the thread is profile
-// traversal index rb + j, memory index n-1-rb-j; j = -1, 8, 9 are the halo its slopes need.  They are
-// staged in memory order: element e = 0..10 is memory index (n-10-rb) + e, i.e. j = 9 - e.
-// EDGE = false: every one of them exists (the bulk of a long profile); A16: the chunk is 16-byte
+// Request the warp's points of one array.  wbase is the profile's memory index of the warp's lowest
+// point (the one furthest along the traversal); chunk c holds memory indices wbase + 2c, + 2c + 1,
+// chunk INV_WCH the two below wbase and chunk INV_WCH + 1 the two from wbase + 256.
+// EDGE = false: every one of them exists (the bulk of a long profile); A16: chunks are 16-byte
 // aligned (even npts, aligned arrays).  EDGE = true: first/last tiles and short profiles, guarded.
 template <bool EDGE, bool A16>
-__device__ __forceinline__ void request_chunk(const double* __restrict__ g, long long n, long long rb,
-                                              double2 (*slot)[INV_BLOCK], int tid) {
-  const double* base = g + (n - INV_ITEMS - 2 - rb);  // element 0
+__device__ __forceinline__ void request_warp(const double* __restrict__ g, long long n, long long wbase,
+                                             double2* buf, unsigned lane) {
+  const double* base = g + wbase;
   if (!EDGE && A16) {
 #pragma unroll
-    for (int q = 0; q < INV_SLOTS - 1; q++) cp_async16(&slot[q][tid], base + 2 * q);
-    cp_async8(&slot[INV_SLOTS - 1][tid].x, base + 2 * (INV_SLOTS - 1), true);
+    for (int q = 0; q < INV_CH; q++) {
+      const int c = 32 * q + (int)lane;
+      cp_async16(&buf[swz(c)], base + 2 * c);
+    }
+    if (lane < 2) cp_async16(&buf[INV_WCH + lane], lane == 0 ? base - 2 : base + INV_WPTS);
   } else {
 #pragma unroll
-    for (int e = 0; e < INV_NP; e++) {
-      bool ok = true;
-      if (EDGE) {
-        const long long r = rb + (INV_ITEMS + 1 - e);
-        ok = r >= 0 && r < n;
+    for (int q = 0; q <= INV_ITEMS; q++) {
+      int e = 32 * q + (int)lane;          // element of the warp's run, memory order
+      double* dst = reinterpret_cast<double*>(&buf[swz(e >> 1)]) + (e & 1);
+      if (q == INV_ITEMS) {                // the halo: elements -2, -1 and 256
+        e = lane == 2 ? INV_WPTS : (int)lane - 2;
+        dst = lane == 2 ? &buf[INV_WCH + 1].x : reinterpret_cast<double*>(&buf[INV_WCH]) + lane;
       }
-      double* dst = reinterpret_cast<double*>(&slot[e >> 1][tid]) + (e & 1);
-      cp_async8(dst, ok ? base + e : g, ok);
+      const long long mi = wbase + e;
+      const bool ok = EDGE ? (mi >= 0 && mi < n) : true;
+      if (q < INV_ITEMS || lane < 3) cp_async8(dst, ok ? base + e : g, ok);
     }
   }
 }
-// ... and pick them up: x[a] is point j = a - 1, element e = 10 - a
-__device__ __forceinline__ void collect_chunk(const double2 (*slot)[INV_BLOCK], int tid, double (&x)[INV_NP]) {
-#pragma unroll
-  for (int q = 0; q < INV_SLOTS; q++) {
-    const double2 v = slot[q][tid];
-    x[INV_NP - 1 - 2 * q] = v.x;
-    if (2 * q + 1 < INV_NP) x[INV_NP - 2 - 2 * q] = v.y;
+// ... and each thread picks up its own: x[a] is point j = a - 1 of the thread
+__device__ __forceinline__ void collect_chunk(const double2* buf, unsigned lane, double (&x)[INV_NP]) {
+  const int u = 31 - (int)lane;
+  {
+    const double2 v = (u == 0) ? buf[INV_WCH] : buf[swz(INV_CH * u - 1)];
+    x[INV_NP - 1] = v.x;
+    x[INV_NP - 2] = v.y;
   }
+#pragma unroll
+  for (int i = 0; i < INV_CH; i++) {
+    const double2 v = buf[swz(INV_CH * u + i)];
+    x[INV_ITEMS - 2 * i] = v.x;
+    x[INV_ITEMS - 1 - 2 * i] = v.y;
+  }
+  x[0] = ((u == 31) ? buf[INV_WCH + 1] : buf[swz(INV_CH * u + INV_CH)]).x;
 }
 
 // What one thread makes of its points:
@@ -334,10 +355,10 @@ __device__ __forceinline__ void look_back(const InvArgs& A, long long p, long lo
 
 template <bool SORP, bool A16>
 __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArgs A) {
-  __shared__ double2 s_in[2][INV_SLOTS][INV_BLOCK];  // the next tile's (theta, o), each thread's own points
+  __shared__ double2 s_in[2][INV_NW][INV_WCH + 2];  // the next tile's (theta, o), each warp's own points
   // A tile's output is written one tile later (see below): its slopes and in-tile prefixes wait here,
-  // each thread's in its own slots.
-  __shared__ double2 s_def[INV_ITEMS][INV_BLOCK];
+  // in the same chunk layout, each warp's own.
+  __shared__ double2 s_dd[INV_NW][INV_WCH], s_ee[INV_NW][INV_WCH];
   __shared__ double s_wt[2][INV_NW];
   __shared__ double s_warp[2][2][INV_NW];
   __shared__ unsigned long long s_tick[2];
@@ -368,17 +389,17 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
   auto request_tile = [&]() {
     p = ticket / A.ntiles;
     t = ticket - p * A.ntiles;
-    const long long rb = t * INV_TILE + (long long)tid * INV_ITEMS;
+    const long long wbase = n - t * INV_TILE - (long long)INV_WPTS * (wid + 1);
     const double* th_g = A.theta + p * n;
     const double* o_g = A.o + p * n;
     dir_a = th_g[n - 2];
     dir_b = th_g[n - 1];
     if (bulk_tile(t)) {
-      request_chunk<false, A16>(th_g, n, rb, s_in[0], tid);
-      request_chunk<false, A16>(o_g, n, rb, s_in[1], tid);
+      request_warp<false, A16>(th_g, n, wbase, s_in[0][wid], lane);
+      request_warp<false, A16>(o_g, n, wbase, s_in[1][wid], lane);
     } else {
-      request_chunk<true, false>(th_g, n, rb, s_in[0], tid);
-      request_chunk<true, false>(o_g, n, rb, s_in[1], tid);
+      request_warp<true, false>(th_g, n, wbase, s_in[0][wid], lane);
+      request_warp<true, false>(o_g, n, wbase, s_in[1][wid], lane);
     }
   };
   if (have) request_tile();
@@ -399,8 +420,9 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       const double dir_step = dir_a - dir_b;
       double x[INV_NP], y[INV_NP];
       cp_async_wait_all();
-      collect_chunk(s_in[0], tid, x);
-      collect_chunk(s_in[1], tid, y);
+      __syncwarp();
+      collect_chunk(s_in[0][wid], lane, x);
+      collect_chunk(s_in[1][wid], lane, y);
       double I[INV_ITEMS], sumF, sumT;
       bool allpos, allneg;
       if (bulk_tile(t)) compute_chunk<false, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, allpos, allneg);
@@ -497,36 +519,32 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
         look_back<1>(A, p2, t2, lane, one);
         prefix = one[0];
       }
-      const long long rb2 = t2 * INV_TILE + (long long)tid * INV_ITEMS;
-
-      // D at the thread's points in the caller's order: traversal point rb2 + j is memory index lo + 7 - j
-      const long long lo = p2 * n + (n - INV_ITEMS - rb2);
-      double Dv[INV_ITEMS], Iv[INV_ITEMS], dv[INV_ITEMS];
+      // D in the caller's order, whole sectors per instruction: lane l takes chunk 32 q + l of the warp's
+      // run (whichever thread computed its slopes), memory indices wb2 + 2c and wb2 + 2c + 1
+      const long long wb2 = n - t2 * INV_TILE - (long long)INV_WPTS * (wid + 1);  // may be < 0 in the last tile
+      __syncwarp();
 #pragma unroll
-      for (int j = 0; j < INV_ITEMS; j++) {
-        const double2 de = s_def[j][tid];
-        dv[j] = de.x;
-        Iv[j] = prefix + de.y;
-        Dv[j] = -(de.x * Iv[j]) * 0.5;
-      }
-      if (A16 && rb2 + INV_ITEMS <= n) {
-#pragma unroll
-        for (int k = 0; k < INV_ITEMS; k += 2)
-          *reinterpret_cast<double2*>(A.D + lo + k) = make_double2(Dv[INV_ITEMS - 1 - k], Dv[INV_ITEMS - 2 - k]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < INV_ITEMS; j++)
-          if (rb2 + j < n) A.D[lo + (INV_ITEMS - 1 - j)] = Dv[j];
-      }
-      if (A.slope) {
-#pragma unroll
-        for (int j = 0; j < INV_ITEMS; j++)
-          if (rb2 + j < n) A.slope[lo + (INV_ITEMS - 1 - j)] = dv[j];
-      }
-      if (A.anti) {
-#pragma unroll
-        for (int j = 0; j < INV_ITEMS; j++)
-          if (rb2 + j < n) A.anti[lo + (INV_ITEMS - 1 - j)] = Iv[j];
+      for (int q = 0; q < INV_CH; q++) {
+        const int c = 32 * q + (int)lane;
+        const long long mi = wb2 + 2 * c;
+        const double2 dd = s_dd[wid][swz(c)], ee = s_ee[wid][swz(c)];
+        const double ix = prefix + ee.x, iy = prefix + ee.y;
+        const double2 Dv = make_double2(-(dd.x * ix) * 0.5, -(dd.y * iy) * 0.5);
+        const long long at = p2 * n + mi;
+        if (A16) {
+          if (mi >= 0) *reinterpret_cast<double2*>(A.D + at) = Dv;
+        } else {
+          if (mi >= 0) A.D[at] = Dv.x;
+          if (mi + 1 >= 0) A.D[at + 1] = Dv.y;
+        }
+        if (A.slope) {
+          if (mi >= 0) A.slope[at] = dd.x;
+          if (mi + 1 >= 0) A.slope[at + 1] = dd.y;
+        }
+        if (A.anti) {
+          if (mi >= 0) A.anti[at] = ix;
+          if (mi + 1 >= 0) A.anti[at + 1] = iy;
+        }
       }
 
       if (closes && lane == 0) {
@@ -569,8 +587,13 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
     }
 
     if (had) {
+      __syncwarp();  // the lanes' reads of the deferred tile above come before these writes
 #pragma unroll
-      for (int j = 0; j < INV_ITEMS; j++) s_def[j][tid] = make_double2(d[j], excl[j]);
+      for (int i = 0; i < INV_CH; i++) {  // chunk 4u + i holds the thread's points j = 7-2i, 6-2i
+        const int c = swz(INV_CH * (31 - (int)lane) + i);
+        s_dd[wid][c] = make_double2(d[INV_ITEMS - 1 - 2 * i], d[INV_ITEMS - 2 - 2 * i]);
+        s_ee[wid][c] = make_double2(excl[INV_ITEMS - 1 - 2 * i], excl[INV_ITEMS - 2 - 2 * i]);
+      }
     }
     pv_p = had ? this_p : -1;
     pv_t = this_t;
