@@ -193,7 +193,9 @@ __device__ __forceinline__ void request_warp(const double* __restrict__ g, long 
       const int c = 32 * q + (int)lane;
       cp_async16(&buf[swz(c)], base + 2 * c);
     }
-    if (lane < 2) cp_async16(&buf[INV_WCH + lane], lane == 0 ? base - 2 : base + INV_WPTS);
+    // the halo; the profile's first tile has nothing above its first warp (and does not use it)
+    if (lane == 0 || (lane == 1 && wbase + INV_WPTS < n))
+      cp_async16(&buf[INV_WCH + lane], lane == 0 ? base - 2 : base + INV_WPTS);
   } else {
 #pragma unroll
     for (int q = 0; q <= INV_ITEMS; q++) {
@@ -204,7 +206,7 @@ __device__ __forceinline__ void request_warp(const double* __restrict__ g, long 
         dst = lane == 2 ? &buf[INV_WCH + 1].x : reinterpret_cast<double*>(&buf[INV_WCH]) + lane;
       }
       const long long mi = wbase + e;
-      const bool ok = EDGE ? (mi >= 0 && mi < n) : true;
+      const bool ok = EDGE ? (mi >= 0 && mi < n) : (mi < n);
       if (q < INV_ITEMS || lane < 3) cp_async8(dst, ok ? base + e : g, ok);
     }
   }
@@ -259,6 +261,14 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, c
     const bool same = (mpos[j] && mpos[j + 1]) || (mneg[j] && mneg[j + 1]);
     d[j] = pchip_interior_steps(hx[j], ho[j], hx[j + 1], ho[j + 1], same);
     if (SORP) df[j] = pchip_interior_steps(ho[j], hx[j], ho[j + 1], hx[j + 1], same);
+    if (!EDGE && j == 0) {
+      // the profile's first point in an otherwise ordinary tile: one-sided, intervals (0,1) and (1,2).
+      // Every later tile of the profile waits for this tile's aggregate, so it takes the fast path too.
+      if (rb == 0) {
+        d[0] = pchip_edge(hx[1], hx[2], ho[1] / hx[1], ho[2] / hx[2]);
+        if (SORP) df[0] = pchip_edge(ho[1], ho[2], hx[1] / ho[1], hx[2] / ho[2]);
+      }
+    }
     if (EDGE) {
       const long long r = rb + j;
       const bool live = r < n, has_left = r >= 1, has_right = r <= n - 2;
@@ -375,9 +385,9 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
   // Tickets are taken one tile ahead (so the requests can be) and in order; aggregates are published
   // before anything is waited for and a blocked CTA only ever holds unpublished tiles LATER than
   // the one it waits on, so the waits cannot form a cycle.
-  auto bulk_tile = [&](long long t) {  // point r0-1 and the points up to r0+TILE+1 exist, r0+TILE is not the last
+  auto bulk_tile = [&](long long t) {  // the points up to r0+TILE+1 exist, r0+TILE is not the last
     const long long r0 = t * INV_TILE;
-    return r0 > 0 && r0 + INV_TILE + 2 <= n;
+    return r0 + INV_TILE + 2 <= n && n > 2;
   };
 
   if (tid == 0) s_tick[0] = atomicAdd(A.ticket, 1ull);
