@@ -40,6 +40,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "fx_math.cuh"
 
@@ -51,6 +52,19 @@ constexpr int INV_TILE = INV_BLOCK * INV_ITEMS;   // 1024 points per tile
 constexpr int INV_NW = INV_BLOCK / 32;
 constexpr int INV_NAGG = 4;  // inverse integral, forward PCHIP integral, trapezoid, flagged-bad count
 constexpr int INV_GROUP = 32; // tiles per look-back group (one warp reads a group)
+#ifndef FX_INV_CTAS
+#define FX_INV_CTAS 4  // resident CTAs per SM the register budget is set for
+#endif
+#ifndef FX_INV_LAG
+#define FX_INV_LAG 3
+#endif
+#ifndef FX_INV_LAG_SORP
+#define FX_INV_LAG_SORP 2
+#endif
+#ifndef FX_INV_DEFER
+#define FX_INV_DEFER 2
+#endif
+constexpr int INV_DEFER = FX_INV_DEFER;  // a tile's output is written this many tiles later
 
 struct InvArgs {
   long long batch, npts, ntiles;      // tiles per profile
@@ -131,21 +145,29 @@ __device__ __forceinline__ double warp_sum(double v) {
 // trip when the value is there instead of three (flag, fence, data), no fence on the reader's
 // side (each 8-byte access is atomic): the look-back sits on every tile's critical path.
 __device__ __forceinline__ bool is_unset(double v) { return __double_as_longlong(v) == -1LL; }
+// A value that is not there yet is polled at a short fixed pause.  The waits sit on the kernel's
+// critical chain (publish -> group total -> look-back -> next publish): pauses of 128 ns and more,
+// or a growing pause, were measured two to three times slower.
+#ifndef FX_INV_NAP
+#define FX_INV_NAP 20
+#endif
 __device__ __forceinline__ void wait_load4(const double* src, double (&v)[4]) {
+  const unsigned nap = FX_INV_NAP;
   for (;;) {
 #pragma unroll
     for (int c = 0; c < 4; c++) v[c] = __ldcg(src + c);
     if (!(is_unset(v[0]) || is_unset(v[1]) || is_unset(v[2]) || is_unset(v[3]))) break;
-    __nanosleep(20);
+    __nanosleep(nap);
   }
 }
 
 __device__ __forceinline__ double wait_load1(const double* src) {
   double v;
+  const unsigned nap = FX_INV_NAP;
   for (;;) {
     v = __ldcg(src);
     if (!is_unset(v)) break;
-    __nanosleep(20);
+    __nanosleep(nap);
   }
   return v;
 }
@@ -169,14 +191,16 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // A WARP owns 32 * INV_ITEMS = 256 consecutive points of the tile and stages them itself, as 16-byte
 // chunks of two points: lane l copies chunk 32 q + l, so one instruction moves 512 contiguous bytes
 // (whole sectors, no reliance on L1), and thread u (in memory order, u = 31 - lane) then reads ITS
-// chunks 4u-1 .. 4u+4.  The chunk position is swizzled within its 128-byte row so that both the
-// copy and the 16-byte reads at a 64-byte stride are free of bank conflicts.  Only the warp reads
+// chunks 4u-1 .. 4u+4.  The rows are padded by one chunk so that both the copy and the 16-byte
+// reads at a 64-byte stride are free of bank conflicts.  Only the warp reads
 // what it staged: cp.async.wait_all + __syncwarp, no CTA barrier.
 static_assert(INV_ITEMS == 8, "the chunk swizzle is laid out for four chunks per thread");
 constexpr int INV_CH = INV_ITEMS / 2;      // chunks per thread
 constexpr int INV_WCH = 32 * INV_CH;       // chunks per warp; two more hold the halo either side
 constexpr int INV_WPTS = 32 * INV_ITEMS;   // points per warp
-__device__ __forceinline__ int swz(int c) { return (c & ~7) | ((c & 7) ^ ((c >> 3) & 3)); }
+// one 16-byte pad per 128-byte row: every address below is a per-thread constant plus an immediate
+__device__ __forceinline__ int swz(int c) { return c + (c >> 3); }
+constexpr int INV_WCHP = INV_WCH + INV_WCH / 8;  // padded chunks per warp
 
 // Request the warp's points of one array.  wbase is the profile's memory index of the warp's lowest
 // point (the one furthest along the traversal); chunk c holds memory indices wbase + 2c, + 2c + 1,
@@ -195,7 +219,7 @@ __device__ __forceinline__ void request_warp(const double* __restrict__ g, long 
     }
     // the halo; the profile's first tile has nothing above its first warp (and does not use it)
     if (lane == 0 || (lane == 1 && wbase + INV_WPTS < n))
-      cp_async16(&buf[INV_WCH + lane], lane == 0 ? base - 2 : base + INV_WPTS);
+      cp_async16(&buf[INV_WCHP + lane], lane == 0 ? base - 2 : base + INV_WPTS);
   } else {
 #pragma unroll
     for (int q = 0; q <= INV_ITEMS; q++) {
@@ -203,7 +227,7 @@ __device__ __forceinline__ void request_warp(const double* __restrict__ g, long 
       double* dst = reinterpret_cast<double*>(&buf[swz(e >> 1)]) + (e & 1);
       if (q == INV_ITEMS) {                // the halo: elements -2, -1 and 256
         e = lane == 2 ? INV_WPTS : (int)lane - 2;
-        dst = lane == 2 ? &buf[INV_WCH + 1].x : reinterpret_cast<double*>(&buf[INV_WCH]) + lane;
+        dst = lane == 2 ? &buf[INV_WCHP + 1].x : reinterpret_cast<double*>(&buf[INV_WCHP]) + lane;
       }
       const long long mi = wbase + e;
       const bool ok = EDGE ? (mi >= 0 && mi < n) : (mi < n);
@@ -215,112 +239,110 @@ __device__ __forceinline__ void request_warp(const double* __restrict__ g, long 
 __device__ __forceinline__ void collect_chunk(const double2* buf, unsigned lane, double (&x)[INV_NP]) {
   const int u = 31 - (int)lane;
   {
-    const double2 v = (u == 0) ? buf[INV_WCH] : buf[swz(INV_CH * u - 1)];
+    const double2 v = (u == 0) ? buf[INV_WCHP] : buf[swz(INV_CH * u - 1)];
     x[INV_NP - 1] = v.x;
     x[INV_NP - 2] = v.y;
   }
 #pragma unroll
   for (int i = 0; i < INV_CH; i++) {
-    const double2 v = buf[swz(INV_CH * u + i)];
+    const double2 v = buf[swz(INV_CH * u) + i];  // the thread's four chunks share a row
     x[INV_ITEMS - 2 * i] = v.x;
     x[INV_ITEMS - 1 - 2 * i] = v.y;
   }
-  x[0] = ((u == 31) ? buf[INV_WCH + 1] : buf[swz(INV_CH * u + INV_CH)]).x;
+  x[0] = ((u == 31) ? buf[INV_WCHP + 1] : buf[swz(INV_CH * u + INV_CH)]).x;
 }
 
 // What one thread makes of its points:
 //   d[j]          do/dtheta at point j = 0..8 (8 closes the thread's last interval)
 //   I[j]          Int o dtheta over the interval (j, j+1), j = 0..7
 //   sumF, sumT    the thread's share of the forward PCHIP and trapezoid integrals of theta do
-//   allpos/allneg whether every interval of the thread steps up / down in theta
+//   mono          whether every interval of the thread steps in theta the way the profile does (up)
 // EDGE = true applies the end-point formulas and drops what lies beyond the profile.
 template <bool EDGE, bool SORP>
 __device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, const double* __restrict__ o_g,
                                               long long n, long long rb, const double (&x)[INV_NP],
                                               const double (&y)[INV_NP], double (&d)[INV_ITEMS + 1],
-                                              double (&I)[INV_ITEMS], double& sumF, double& sumT, bool& allpos,
-                                              bool& allneg) {
-  // signed steps and the strict sign of each interval's secant
-  double hx[INV_NI], ho[INV_NI];
-  bool mpos[INV_NI], mneg[INV_NI], xpos[INV_NI], xneg[INV_NI];
-#pragma unroll
-  for (int b = 0; b < INV_NI; b++) {
-    hx[b] = x[b + 1] - x[b];
-    ho[b] = y[b + 1] - y[b];
-    xpos[b] = hx[b] > 0.0;
-    xneg[b] = hx[b] < 0.0;
-    const bool opos = ho[b] > 0.0, oneg = ho[b] < 0.0;
-    mpos[b] = (xpos[b] && opos) || (xneg[b] && oneg);
-    mneg[b] = (xpos[b] && oneg) || (xneg[b] && opos);
-  }
-
-  // slopes at j = 0..8: intervals b = j (before) and b = j+1 (after)
-  double df[INV_ITEMS + 1];
+                                              double (&I)[INV_ITEMS], double& sumF, double& sumT, bool up,
+                                              bool& mono) {
+  // One pass along the thread's points, each step using what the one before left behind: the interval
+  // after point j (its steps and a number with the sign of its secant -- steps of 1e-77 would have to
+  // meet for that product to underflow), the slope at j, the integral over the interval before j.
+  // The empty asm statements pin this order: left to itself the compiler interleaves all nine slopes
+  // and needs 170 registers for it.
+  sumF = 0.0;
+  sumT = 0.0;
+  mono = true;
+  double hc = x[1] - x[0], gc = y[1] - y[0];  // interval before point 0
+  double sc = hc * gc;
+  double dprev = 0.0, dfprev = 0.0;
 #pragma unroll
   for (int j = 0; j <= INV_ITEMS; j++) {
-    const bool same = (mpos[j] && mpos[j + 1]) || (mneg[j] && mneg[j + 1]);
-    d[j] = pchip_interior_steps(hx[j], ho[j], hx[j + 1], ho[j + 1], same);
-    if (SORP) df[j] = pchip_interior_steps(ho[j], hx[j], ho[j + 1], hx[j + 1], same);
+    double xn = x[j + 2], yn = y[j + 2];
+    {  // step j starts when the slope of step j - LAG is known: LAG steps in flight
+      constexpr int LAG = SORP ? FX_INV_LAG_SORP : FX_INV_LAG;
+      const double dep = j >= LAG ? d[j - LAG] : 0.0;
+      asm volatile("" : "+d"(xn), "+d"(yn) : "d"(dep));
+    }
+    const double hn = xn - x[j + 1], gn = yn - y[j + 1];  // interval after point j
+    const double sn = hn * gn;
+    const bool same = sc * sn > 0.0;  // the two secants have the same strict sign
+    double dj = pchip_interior_steps(hc, gc, hn, gn, same);
+    double dfj = 0.0;
+    if (SORP) dfj = pchip_interior_steps(gc, hc, gn, hn, same);
     if (!EDGE && j == 0) {
       // the profile's first point in an otherwise ordinary tile: one-sided, intervals (0,1) and (1,2).
       // Every later tile of the profile waits for this tile's aggregate, so it takes the fast path too.
       if (rb == 0) {
-        d[0] = pchip_edge(hx[1], hx[2], ho[1] / hx[1], ho[2] / hx[2]);
-        if (SORP) df[0] = pchip_edge(ho[1], ho[2], hx[1] / ho[1], hx[2] / ho[2]);
+        const double h2 = x[3] - x[2], g2 = y[3] - y[2];
+        dj = pchip_edge(hn, h2, gn / hn, g2 / h2);
+        if (SORP) dfj = pchip_edge(gn, g2, hn / gn, h2 / g2);
       }
     }
     if (EDGE) {
       const long long r = rb + j;
       const bool live = r < n, has_left = r >= 1, has_right = r <= n - 2;
       if (!live) {
-        d[j] = 0.0;
-        if (SORP) df[j] = 0.0;
+        dj = 0.0;
+        dfj = 0.0;
       } else if (!(has_left && has_right)) {
         if (n == 2) {
-          d[j] = has_right ? ho[j + 1] / hx[j + 1] : ho[j] / hx[j];
-          if (SORP) df[j] = has_right ? hx[j + 1] / ho[j + 1] : hx[j] / ho[j];
-        } else if (has_right) {  // r == 0, one-sided: intervals (0,1) and (1,2), both staged (every later
-          // tile of the profile waits for this one: nothing here goes back to global memory)
-          const int b2 = j + 2 < INV_NI ? j + 2 : INV_NI - 1;  // r == 0 is the j = 0 of one thread
-          const double a1 = hx[j + 1], a2 = hx[b2], c1 = ho[j + 1], c2 = ho[b2];
-          d[j] = pchip_edge(a1, a2, c1 / a1, c2 / a2);
-          if (SORP) df[j] = pchip_edge(c1, c2, a1 / c1, a2 / c2);
+          dj = has_right ? gn / hn : gc / hc;
+          if (SORP) dfj = has_right ? hn / gn : hc / gc;
+        } else if (has_right) {  // r == 0, one-sided: intervals (0,1) and (1,2), both staged
+          const int a2 = j + 3 < INV_NP ? j + 3 : INV_NP - 1;  // r == 0 is the j = 0 of one thread
+          const double h2 = x[a2] - x[a2 - 1], g2 = y[a2] - y[a2 - 1];
+          dj = pchip_edge(hn, h2, gn / hn, g2 / h2);
+          if (SORP) dfj = pchip_edge(gn, g2, hn / gn, h2 / g2);
         } else {  // r == n-1, one-sided, mirrored: intervals (n-2,n-1) and (n-3,n-2)
           const double x0 = th_g[0], x1 = th_g[1], x2 = th_g[2];
           const double y0 = o_g[0], y1 = o_g[1], y2 = o_g[2];
-          const double a1 = x0 - x1, a2 = x1 - x2, c1 = y0 - y1, c2 = y1 - y2;
-          d[j] = pchip_edge(a1, a2, c1 / a1, c2 / a2);
-          if (SORP) df[j] = pchip_edge(c1, c2, a1 / c1, a2 / c2);
+          const double a1 = x0 - x1, a2_ = x1 - x2, c1 = y0 - y1, c2 = y1 - y2;
+          dj = pchip_edge(a1, a2_, c1 / a1, c2 / a2_);
+          if (SORP) dfj = pchip_edge(c1, c2, a1 / c1, a2_ / c2);
         }
       }
     }
-  }
-
-  // per-interval cubic-Hermite integrals, intervals j = 0..7 (b = j+1)
-  sumF = 0.0;
-  sumT = 0.0;
-  allpos = true;
-  allneg = true;
-#pragma unroll
-  for (int j = 0; j < INV_ITEMS; j++) {
-    const int b = j + 1;
-    const double h = hx[b];
-    double v = h * fma(0.5, y[b] + y[b + 1], (d[j] - d[j + 1]) * (h * (1.0 / 12.0)));
-    bool exists = true;
-    if (EDGE) exists = rb + j <= n - 2;
-    I[j] = exists ? v : 0.0;
-    if (exists) {
-      allpos = allpos && xpos[b];
-      allneg = allneg && xneg[b];
-    }
-    if (SORP) {
-      const double g = ho[b];
-      const double trap = g * (0.5 * (x[b] + x[b + 1]));
-      if (exists) {
-        sumT += trap;
-        sumF += fma((df[j] - df[j + 1]) * g, g * (1.0 / 12.0), trap);
+    d[j] = dj;
+    if (j >= 1) {  // cubic-Hermite integral over the interval (j-1, j), whose steps are (hc, gc)
+      double v = hc * fma(0.5, y[j] + y[j + 1], (dprev - dj) * (hc * (1.0 / 12.0)));
+      bool exists = true;
+      if (EDGE) exists = rb + j - 1 <= n - 2;
+      v = exists ? v : 0.0;
+      if (exists) mono = mono && (up ? hc > 0.0 : hc < 0.0);
+      if (SORP) {
+        const double trap = gc * (0.5 * (x[j] + x[j + 1]));
+        if (exists) {
+          sumT += trap;
+          sumF += fma((dfprev - dfj) * gc, gc * (1.0 / 12.0), trap);
+        }
       }
+      I[j - 1] = v;
     }
+    hc = hn;
+    gc = gn;
+    sc = sn;
+    dprev = dj;
+    dfprev = dfj;
   }
 }
 
@@ -364,17 +386,19 @@ __device__ __forceinline__ void look_back(const InvArgs& A, long long p, long lo
 }
 
 template <bool SORP, bool A16>
-__global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArgs A) {
-  __shared__ double2 s_in[2][INV_NW][INV_WCH + 2];  // the next tile's (theta, o), each warp's own points
+__global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(const InvArgs A) {
+  __shared__ double2 s_in[2][INV_NW][INV_WCHP + 2];  // the next tile's (theta, o), each warp's own points
   // A tile's output is written one tile later (see below): its slopes and in-tile prefixes wait here,
   // in the same chunk layout, each warp's own.
-  __shared__ double2 s_dd[INV_NW][INV_WCH], s_ee[INV_NW][INV_WCH];
   __shared__ double s_wt[2][INV_NW];
   __shared__ double s_warp[2][2][INV_NW];
   __shared__ unsigned long long s_tick[2];
 
   const int tid = threadIdx.x;
   const unsigned lane = tid & 31, wid = tid >> 5;
+  extern __shared__ double2 s_dyn[];  // [INV_DEFER][2][INV_NW][INV_WCH]: slopes and in-tile prefixes of the deferred tiles
+  auto s_dd = [&](int slot) { return s_dyn + ((size_t)(slot * 2 + 0) * INV_NW + wid) * INV_WCH; };
+  auto s_ee = [&](int slot) { return s_dyn + ((size_t)(slot * 2 + 1) * INV_NW + wid) * INV_WCH; };
   const long long total_tiles = A.batch * A.ntiles;
   const long long n = A.npts;
 
@@ -414,11 +438,15 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
   };
   if (have) request_tile();
 
-  long long pv_p = -1, pv_t = 0;  // the deferred tile
+  // the deferred tiles, oldest first; tile number k of this CTA keeps its data in slot k % INV_DEFER
+  long long pv_p[INV_DEFER], pv_t[INV_DEFER];
+#pragma unroll
+  for (int q = 0; q < INV_DEFER; q++) pv_p[q] = -1, pv_t[q] = 0;
+  int slot = 0;
   int par = 0;
 
   for (;;) {
-    if (!have && pv_p < 0) break;
+    if (!have && pv_p[0] < 0 && pv_p[INV_DEFER - 1] < 0) break;
     if (tid == 0 && have) s_tick[par ^ 1] = atomicAdd(A.ticket, 1ull);
     double d[INV_ITEMS + 1], excl[INV_ITEMS];
     double run = 0.0, wincl = 0.0;
@@ -434,11 +462,11 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       collect_chunk(s_in[0][wid], lane, x);
       collect_chunk(s_in[1][wid], lane, y);
       double I[INV_ITEMS], sumF, sumT;
-      bool allpos, allneg;
-      if (bulk_tile(t)) compute_chunk<false, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, allpos, allneg);
-      else compute_chunk<true, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, allpos, allneg);
+      bool mono;
       const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);
-      bad = flat || !(up ? allpos : allneg);
+      if (bulk_tile(t)) compute_chunk<false, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
+      else compute_chunk<true, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
+      bad = flat || !mono;
 
       // in-thread running sums, then one warp scan of the thread totals
 #pragma unroll
@@ -517,8 +545,8 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
     }
 
     // ---- the deferred tile: every warp sums the earlier tiles of its profile, then writes its output --
-    if (pv_p >= 0) {
-      const long long p2 = pv_p, t2 = pv_t;
+    if (pv_p[0] >= 0) {
+      const long long p2 = pv_p[0], t2 = pv_t[0];
       const bool closes = (t2 == A.ntiles - 1) && wid == 0;  // the last tile of a profile closes its sums
       double prefix, tot[INV_NAGG];
       if (closes) {
@@ -533,27 +561,41 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       // run (whichever thread computed its slopes), memory indices wb2 + 2c and wb2 + 2c + 1
       const long long wb2 = n - t2 * INV_TILE - (long long)INV_WPTS * (wid + 1);  // may be < 0 in the last tile
       __syncwarp();
+      // the stash is XOR-swizzled within its 128-byte rows (no padding: two deferred tiles must fit):
+      // chunk 32 q + lane sits at 32 q + xl
+      const int xl = ((int)lane & ~7) | (((int)lane & 7) ^ (((int)lane >> 3) & 3));
+      const double2* sd = s_dd(slot) + xl;
+      const double2* se = s_ee(slot) + xl;
+      const long long at0 = p2 * n + wb2 + 2 * (long long)lane;  // chunk q of the lane starts at at0 + 64 q
+      if (A16 && wb2 >= 0 && !A.slope && !A.anti) {  // all but a profile's last tile: nothing to guard
+        double2* Dp = reinterpret_cast<double2*>(A.D + at0);
 #pragma unroll
-      for (int q = 0; q < INV_CH; q++) {
-        const int c = 32 * q + (int)lane;
-        const long long mi = wb2 + 2 * c;
-        const double2 dd = s_dd[wid][swz(c)], ee = s_ee[wid][swz(c)];
-        const double ix = prefix + ee.x, iy = prefix + ee.y;
-        const double2 Dv = make_double2(-(dd.x * ix) * 0.5, -(dd.y * iy) * 0.5);
-        const long long at = p2 * n + mi;
-        if (A16) {
-          if (mi >= 0) *reinterpret_cast<double2*>(A.D + at) = Dv;
-        } else {
-          if (mi >= 0) A.D[at] = Dv.x;
-          if (mi + 1 >= 0) A.D[at + 1] = Dv.y;
+        for (int q = 0; q < INV_CH; q++) {
+          const double2 dd = sd[q * 32], ee = se[q * 32];
+          Dp[32 * q] = make_double2(-(dd.x * (prefix + ee.x)) * 0.5, -(dd.y * (prefix + ee.y)) * 0.5);
         }
-        if (A.slope) {
-          if (mi >= 0) A.slope[at] = dd.x;
-          if (mi + 1 >= 0) A.slope[at + 1] = dd.y;
-        }
-        if (A.anti) {
-          if (mi >= 0) A.anti[at] = ix;
-          if (mi + 1 >= 0) A.anti[at + 1] = iy;
+      } else {
+#pragma unroll
+        for (int q = 0; q < INV_CH; q++) {
+          const long long mi = wb2 + 2 * (32 * q + (long long)lane);
+          const double2 dd = sd[q * 32], ee = se[q * 32];
+          const double ix = prefix + ee.x, iy = prefix + ee.y;
+          const double2 Dv = make_double2(-(dd.x * ix) * 0.5, -(dd.y * iy) * 0.5);
+          const long long at = at0 + 64 * q;
+          if (A16) {
+            if (mi >= 0) *reinterpret_cast<double2*>(A.D + at) = Dv;
+          } else {
+            if (mi >= 0) A.D[at] = Dv.x;
+            if (mi + 1 >= 0) A.D[at + 1] = Dv.y;
+          }
+          if (A.slope) {
+            if (mi >= 0) A.slope[at] = dd.x;
+            if (mi + 1 >= 0) A.slope[at + 1] = dd.y;
+          }
+          if (A.anti) {
+            if (mi >= 0) A.anti[at] = ix;
+            if (mi + 1 >= 0) A.anti[at + 1] = iy;
+          }
         }
       }
 
@@ -600,13 +642,17 @@ __global__ void __launch_bounds__(INV_BLOCK, 4) inverse_scan_kernel(const InvArg
       __syncwarp();  // the lanes' reads of the deferred tile above come before these writes
 #pragma unroll
       for (int i = 0; i < INV_CH; i++) {  // chunk 4u + i holds the thread's points j = 7-2i, 6-2i
-        const int c = swz(INV_CH * (31 - (int)lane) + i);
-        s_dd[wid][c] = make_double2(d[INV_ITEMS - 1 - 2 * i], d[INV_ITEMS - 2 - 2 * i]);
-        s_ee[wid][c] = make_double2(excl[INV_ITEMS - 1 - 2 * i], excl[INV_ITEMS - 2 - 2 * i]);
+        const int u = 31 - (int)lane;
+        const int c = INV_CH * u + (i ^ ((u >> 1) & 3));  // chunk 4u + i, XOR-swizzled: stays within the thread's four
+        s_dd(slot)[c] = make_double2(d[INV_ITEMS - 1 - 2 * i], d[INV_ITEMS - 2 - 2 * i]);
+        s_ee(slot)[c] = make_double2(excl[INV_ITEMS - 1 - 2 * i], excl[INV_ITEMS - 2 - 2 * i]);
       }
     }
-    pv_p = had ? this_p : -1;
-    pv_t = this_t;
+#pragma unroll
+    for (int q = 0; q + 1 < INV_DEFER; q++) pv_p[q] = pv_p[q + 1], pv_t[q] = pv_t[q + 1];
+    pv_p[INV_DEFER - 1] = had ? this_p : -1;
+    pv_t[INV_DEFER - 1] = this_t;
+    slot = (slot + 1 == INV_DEFER) ? 0 : slot + 1;
     par ^= 1;
   }
 }
@@ -737,14 +783,25 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   const bool a16 = (npts % 2 == 0) && ((((uintptr_t)o | (uintptr_t)theta | (uintptr_t)D) & 15) == 0);
   void (*kern)(const InvArgs) = sorp ? (a16 ? inverse_scan_kernel<true, true> : inverse_scan_kernel<true, false>)
                                      : (a16 ? inverse_scan_kernel<false, true> : inverse_scan_kernel<false, false>);
+  const size_t dyn = (size_t)INV_DEFER * 2 * INV_NW * INV_WCH * sizeof(double2);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return e;
+  {
+    const char* co = getenv("FX_INV_CARVEOUT");
+    const int pct = co ? atoi(co) : 100;
+    if (pct >= 0) {
+      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+      if (e != cudaSuccess) return e;
+    }
+  }
   int bps = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, INV_BLOCK, 0);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, INV_BLOCK, dyn);
   if (e != cudaSuccess) return e;
   if (bps < 1) bps = 1;
   long long cap = (long long)sms * bps;
   int grid = (int)((long long)tiles < cap ? (long long)tiles : cap);
   if (grid < 1) grid = 1;
-  kern<<<grid, INV_BLOCK, 0, s>>>(a);
+  kern<<<grid, INV_BLOCK, dyn, s>>>(a);
   *launches = 1;
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
