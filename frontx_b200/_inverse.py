@@ -31,6 +31,8 @@ class BatchInverse:
 
     def D(self, theta_query: Any):
         """InterpolatedSolution.D at theta_query[batch, q] (NaN outside each profile's range)."""
+        if self._slope is None:
+            raise ValueError("this inverse was computed with query=False: D at the knots only")
         torch = _lib.require_cuda()
         dev = self.o.device
         tq = torch.as_tensor(theta_query, dtype=torch.float64, device=dev)
@@ -47,14 +49,20 @@ class BatchInverse:
                                                          torch.cuda.current_stream(dev).cuda_stream))
         return out
 
+    def _need_sorp(self):
+        if self._sorp is None:
+            raise ValueError("this inverse was computed with sorptivity=False: D only")
+
     def sorptivity(self):
         """InterpolatedSolution.sorptivity(o=0) per profile (interpolated.py:69-73)."""
+        self._need_sorp()
         oi = self.o[:, -1]
         i = self.theta[:, -1]
         return (self._sorp[:, 0] + self._sorp[:, 2]) - i * oi
 
     def sorptivity_trapezoid(self, b: Any, i: Any):
         """frontx.sorptivity(o, theta, b=, i=) per profile (_inverse/sorptivity.py:16-19)."""
+        self._need_sorp()
         torch = _lib.require_cuda()
         dev = self.o.device
         b_ = torch.as_tensor(b, dtype=torch.float64, device=dev)
@@ -64,10 +72,14 @@ class BatchInverse:
         return self._sorp[:, 1] + 0.5 * (th0 + b_) * o0 - i_ * oi
 
 
-def inverse(o: Any, theta: Any, *, device: Any = None, throw: bool = True) -> BatchInverse:
+def inverse(o: Any, theta: Any, *, device: Any = None, throw: bool = True, sorptivity: bool = True,
+            query: bool = True) -> BatchInverse:
     """``InterpolatedSolution(o, theta).D`` for a batch of profiles, on the GPU.
 
     ``o`` and ``theta`` are [batch, npts] (or [npts]); numpy arrays or CUDA tensors.
+    ``sorptivity=False`` skips the sorptivity integrals of the forward interpolant (a second PCHIP
+    slope per point: a quarter of the kernel's time), ``query=False`` the two knot arrays that
+    ``BatchInverse.D(theta_query)`` needs (16 B/point more written): D at the knots only.
     """
     torch = _lib.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -80,14 +92,15 @@ def inverse(o: Any, theta: Any, *, device: Any = None, throw: bool = True) -> Ba
     o_t, th_t = o_t.contiguous(), th_t.contiguous()
     batch, npts = o_t.shape
     D = torch.empty_like(o_t)
-    slope = torch.empty_like(o_t)
-    anti = torch.empty_like(o_t)
-    sorp = torch.empty((batch, 4), dtype=torch.float64, device=dev)
+    slope = torch.empty_like(o_t) if query else None
+    anti = torch.empty_like(o_t) if query else None
+    sorp = torch.empty((batch, 4), dtype=torch.float64, device=dev) if sorptivity else None
     status = torch.empty((batch,), dtype=torch.int32, device=dev)
+    ptr = lambda x: None if x is None else x.data_ptr()  # noqa: E731
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().fx_inverse_batch(batch, npts, o_t.data_ptr(), th_t.data_ptr(), D.data_ptr(),
-                                               sorp.data_ptr(), status.data_ptr(), slope.data_ptr(),
-                                               anti.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+                                               ptr(sorp), status.data_ptr(), ptr(slope), ptr(anti),
+                                               torch.cuda.current_stream(dev).cuda_stream))
     res = BatchInverse(o_t, th_t, D, sorp, status, slope, anti)
     if throw and int(status.sum().item()) != 0:
         raise ValueError("theta must be strictly monotone in o for every profile")

@@ -163,7 +163,9 @@ int fx_diffusivity_batch(int64_t n, const int32_t *model_id, const double *param
  * for `batch` profiles of `npts` points each, theta strictly monotone in o:
  *   D_at_knots [batch][npts]  InterpolatedSolution.D at every data point, caller's order  (:59-67)
  *   sorptivity [batch][4]     {PCHIP Int theta do over the data (:69-73), trapezoid Int theta do
- *                              (_inverse/sorptivity.py:16-19), PCHIP-extrapolated Int_0^o[0], 0}
+ *                              (_inverse/sorptivity.py:16-19), PCHIP-extrapolated Int_0^o[0], 0};
+ *                              optional (NULL to skip: the forward interpolant's slopes are then
+ *                              not formed at all, a quarter of the kernel's time)
  *   status     [batch]        0 ok, 1 theta not strictly monotone (D is then meaningless)
  *   do_dtheta, Iodtheta [batch][npts], optional (NULL to skip): the inverse PCHIP's knot
  *                              slopes and antiderivative values (minus its value at theta=i),

@@ -489,6 +489,61 @@ def test_inverse_query_vs_scipy_twin():
     np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-12 * np.abs(want).max())
 
 
+def test_inverse_D_only_equals_full_and_odd_lengths(fxo):
+    """The D-only launch (no sorptivity sums, no query arrays) gives the same D bit for bit; odd npts and
+    an offset base pointer take the 8-byte (unaligned) instantiation and agree with the aligned one."""
+    rng = np.random.default_rng(8)
+    for npts in (4096, 4097, 5000, 1023, 7):
+        a = rng.uniform(0.5, 2.0, 5)
+        o = np.stack([np.linspace(0, 12 / x, npts) for x in a])
+        th = 0.05 + 0.9 * np.exp(-a[:, None] * o)
+        full = fx.inverse(o, th)
+        lean = fx.inverse(o, th, sorptivity=False, query=False)
+        np.testing.assert_array_equal(full.D_at_knots.cpu().numpy(), lean.D_at_knots.cpu().numpy())
+        with pytest.raises(ValueError):
+            lean.sorptivity()
+        with pytest.raises(ValueError):
+            lean.D(th[:, :3])
+        for j in (0, 4):
+            rc, D_c, s_pchip, _ = fxo.inverse(o[j], th[j])
+            np.testing.assert_allclose(full.D_at_knots[j].cpu().numpy(), D_c, rtol=1e-9, atol=1e-12 * np.abs(D_c).max())
+            assert float(full.sorptivity()[j]) == pytest.approx(s_pchip, rel=1e-9)
+    # a view that starts 8 bytes into an allocation: unaligned rows even though npts is even
+    import torch
+
+    npts = 6000
+    o1 = np.linspace(0, 9, npts)
+    th1 = np.exp(-0.7 * o1)
+    pad_o = torch.zeros(npts + 1, dtype=torch.float64, device="cuda")
+    pad_t = torch.zeros(npts + 1, dtype=torch.float64, device="cuda")
+    pad_o[1:] = torch.as_tensor(o1, device="cuda")
+    pad_t[1:] = torch.as_tensor(th1, device="cuda")
+    shifted = fx.inverse(pad_o[1:], pad_t[1:])
+    plain = fx.inverse(o1, th1)
+    np.testing.assert_array_equal(shifted.D_at_knots.cpu().numpy(), plain.D_at_knots.cpu().numpy())
+    np.testing.assert_array_equal(shifted._sorp.cpu().numpy(), plain._sorp.cpu().numpy())
+
+
+def test_inverse_long_increasing_and_non_monotone_in_the_bulk(fxo):
+    """Tiles away from a profile's ends take the unguarded path: an increasing profile, and one flat
+    step deep inside a long profile, must come out as on the guarded path."""
+    o = np.linspace(0, 3, 9000)
+    th = 0.2 + 0.5 * np.tanh(o)
+    rc, D_c, s_pchip, _ = fxo.inverse(o, th)
+    res = fx.inverse(o, th)
+    np.testing.assert_allclose(res.D_at_knots[0].cpu().numpy(), D_c, rtol=1e-9, atol=1e-12 * np.abs(D_c).max())
+    assert float(res.sorptivity()[0]) == pytest.approx(s_pchip, rel=1e-9)
+    for where in (3000, 4095, 4096, 4097, 8998):
+        bad = np.exp(-np.linspace(0, 5, 9000))
+        bad[where] = bad[where - 1]
+        both = np.stack([np.exp(-np.linspace(0, 5, 9000)), bad])
+        st = fx.inverse(np.stack([np.linspace(0, 5, 9000)] * 2), both, throw=False).status.cpu().numpy()
+        assert st.tolist() == [0, 1]
+        up = bad[::-1].copy()  # the same flaw in an increasing profile
+        st = fx.inverse(np.linspace(0, 5, 9000), up, throw=False).status.cpu().numpy()
+        assert st.tolist() == [1]
+
+
 def test_inverse_rejects_non_monotone():
     o = np.linspace(0, 5, 64)
     th = np.exp(-o)
