@@ -16,18 +16,19 @@
 // decreasing profile and its exact mirror for an increasing one.
 //
 // Algorithmic traffic: 16 B/point read (o, theta), 8 B/point written (D); every point is
-// read once (plus a 3-point halo per thread, which hits L1).  One CTA owns a tile of INV_TILE
-// consecutive points of one profile, one THREAD a chunk of INV_ITEMS consecutive points, held in
-// registers from the 16-byte global loads to the 16-byte global stores (no shared-memory staging):
+// read once (plus a 3-point halo per warp), measured DRAM traffic equals it.  One CTA owns a tile of
+// INV_TILE consecutive points of one profile, one WARP 256 of them, one THREAD a chunk of INV_ITEMS
+// consecutive points, which it keeps in registers:
+//   the warp stages its points with coalesced cp.async, a tile ahead (request_warp / collect_chunk)
 //   steps (d theta, d o) of the chunk's intervals and the two either side
 //   PCHIP slope do/dtheta at the chunk's points (and dtheta/do when the sorptivity is wanted)
 //   per-interval cubic-Hermite integrals; running sum in the thread, one warp scan of the thread
-//   totals, the four warp totals through shared memory
-//   publish the tile aggregate, go on to the next tile, then add up the aggregates of all
+//   totals, the four warp totals through shared memory (the tile's only barrier)
+//   publish the tile aggregate, go on to the next two tiles, then add up the aggregates of all
 //   EARLIER tiles of the profile in a fixed two-level order (tickets are handed out in order,
 //   so every earlier tile is resident or finished: no deadlock, no serial chain, and the
 //   result is bit-reproducible run to run)
-//   D = -d * (prefix + local)/2, written in the caller's point order.
+//   D = -d * (prefix + local)/2, written coalesced in the caller's point order.
 //
 // Arithmetic: an fp64 division costs ~25 issue slots on sm_100a (scripts/ubench_fp64.cu), and
 // scipy's formulas written literally take 12 per point, which made the first version of this
