@@ -433,6 +433,13 @@ def inverse_profiles():
     yield "tile boundary 1024", np.linspace(0, 5, 1024), np.exp(-np.linspace(0, 5, 1024))
     yield "tile boundary 1025", np.linspace(0, 5, 1025), np.exp(-np.linspace(0, 5, 1025))
     yield "tile boundary 2049", np.linspace(0, 5, 2049), np.exp(-np.linspace(0, 5, 2049))
+    # more than 32 tiles of 1024 points: the two-level look-back (group totals) comes into play
+    o6 = np.linspace(0, 20 / 0.9, 100_000)
+    yield "three full groups 100k", o6, np.exp(-0.9 * o6)
+    o7 = np.linspace(0, 14, 70_001)
+    yield "two groups, odd length 70001", o7, 0.3 + 0.6 / (1.0 + o7) ** 3
+    o8 = np.linspace(0, 4, 32 * 1024 + 1)
+    yield "exactly one group + 1", o8, 0.1 + 0.7 * np.tanh(o8)
 
 
 @pytest.mark.parametrize("case", list(inverse_profiles()), ids=lambda c: c[0])
@@ -522,6 +529,27 @@ def test_inverse_D_only_equals_full_and_odd_lengths(fxo):
     plain = fx.inverse(o1, th1)
     np.testing.assert_array_equal(shifted.D_at_knots.cpu().numpy(), plain.D_at_knots.cpu().numpy())
     np.testing.assert_array_equal(shifted._sorp.cpu().numpy(), plain._sorp.cpu().numpy())
+
+
+def test_inverse_many_long_profiles_reproducible_and_equal_to_single(fxo):
+    """300 profiles x 40 000 points keep every SM busy with tiles of different profiles and groups: each
+    profile must come out exactly as when it is solved alone, run after run."""
+    rng = np.random.default_rng(11)
+    a = rng.uniform(0.5, 2.0, 300)
+    o = np.linspace(0, 20, 40_000)[None, :] / a[:, None]
+    th = np.exp(-a[:, None] * o)
+    first = fx.inverse(o, th)
+    D = first.D_at_knots.cpu().numpy()
+    again = fx.inverse(o, th)
+    np.testing.assert_array_equal(D, again.D_at_knots.cpu().numpy())
+    np.testing.assert_array_equal(first._sorp.cpu().numpy(), again._sorp.cpu().numpy())
+    for j in (0, 151, 299):
+        alone = fx.inverse(o[j], th[j])
+        np.testing.assert_array_equal(D[j], alone.D_at_knots[0].cpu().numpy())
+        rc, D_c, s_pchip, s_trapz = fxo.inverse(o[j], th[j])
+        np.testing.assert_allclose(D[j], D_c, rtol=1e-9, atol=1e-12 * np.abs(D_c).max())
+        assert float(first.sorptivity()[j]) == pytest.approx(s_pchip, rel=1e-9)
+        assert float(first._sorp[j, 1]) == pytest.approx(s_trapz, rel=1e-12)
 
 
 def test_inverse_long_increasing_and_non_monotone_in_the_bulk(fxo):
