@@ -386,6 +386,31 @@ __device__ __forceinline__ void look_back(const InvArgs& A, long long p, long lo
   for (int c = 0; c < NC; c++) part[c] = warp_sum(part[c]);
 }
 
+// Int_0^{o_first} of the forward PCHIP's first cubic extrapolated back to o = 0 (scipy extrapolate=True)
+__device__ __forceinline__ double pchip_extrapolated_head(const double* o_g, const double* th_g, long long n) {
+  double ext = 0.0;
+  double o0 = o_g[0];
+  if (o0 != 0.0 && n >= 2) {
+    double o1 = o_g[1], y0 = th_g[0], y1 = th_g[1];
+    double hh = o1 - o0, m = (y1 - y0) / hh;
+    double d0, d1;
+    if (n == 2) {
+      d0 = d1 = m;
+    } else {
+      double o2 = o_g[2], y2 = th_g[2];
+      double h1 = o2 - o1, m1 = (y2 - y1) / h1;
+      d0 = pchip_edge(hh, h1, m, m1);
+      d1 = (n == 3) ? pchip_edge(h1, hh, m1, m) : pchip_interior(hh, h1, m, m1);
+    }
+    double tt = (d0 + d1 - 2.0 * m) / hh;
+    double c0 = tt / hh, c1 = (m - d0) / hh - tt, c2 = d0, c3 = y0;
+    double u = 0.0 - o0;  // antiderivative at o=0 relative to o0
+    double anti = (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + c2 * 0.5) * u + c3) * u;
+    ext = -anti;
+  }
+  return ext;
+}
+
 template <bool SORP, bool A16>
 __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(const InvArgs A) {
   __shared__ double2 s_in[2][INV_NW][INV_WCHP + 2];  // the next tile's (theta, o), each warp's own points
@@ -612,28 +637,7 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
           double* out = A.sorp + p2 * 4;
           out[0] = -F;
           out[1] = -Z;
-          // extrapolation of the first forward cubic from o_first back to 0 (scipy extrapolate=True)
-          double ext = 0.0;
-          double o0 = o_g[0];
-          if (o0 != 0.0 && n >= 2) {
-            double o1 = o_g[1], y0 = th_g[0], y1 = th_g[1];
-            double hh = o1 - o0, m = (y1 - y0) / hh;
-            double d0, d1;
-            if (n == 2) {
-              d0 = d1 = m;
-            } else {
-              double o2 = o_g[2], y2 = th_g[2];
-              double h1 = o2 - o1, m1 = (y2 - y1) / h1;
-              d0 = pchip_edge(hh, h1, m, m1);
-              d1 = (n == 3) ? pchip_edge(h1, hh, m1, m) : pchip_interior(hh, h1, m, m1);
-            }
-            double tt = (d0 + d1 - 2.0 * m) / hh;
-            double c0 = tt / hh, c1 = (m - d0) / hh - tt, c2 = d0, c3 = y0;
-            double u = 0.0 - o0;  // antiderivative at o=0 relative to o0
-            double anti = (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + c2 * 0.5) * u + c3) * u;
-            ext = -anti;  // Int_0^{o0}
-          }
-          out[2] = ext;
+          out[2] = pchip_extrapolated_head(o_g, th_g, n);
           out[3] = 0.0;
         }
       }
@@ -655,6 +659,293 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
     pv_t[INV_DEFER - 1] = this_t;
     slot = (slot + 1 == INV_DEFER) ? 0 : slot + 1;
     par ^= 1;
+  }
+}
+
+// ---- the same scan with WARP-sized tiles: no CTA barrier at all ---------------------------------------
+// Every warp is on its own: it takes tickets for tiles of 256 points, stages, computes, publishes and
+// looks back by itself.  Four times as many tiles, so the look-back has three fixed levels: aggregates of
+// the earlier tiles of the group of 32, totals of the earlier groups of the supergroup of 32 groups, totals
+// of the earlier supergroups.  Whoever ARRIVES last in a group (supergroup) publishes its total.  (Letting
+// the tile that is last by index wait for the others was measured at 450 ms: it waits, in line, for tiles
+// that other warps hold as their NEXT ticket, and everything behind its own next ticket waits with it.)
+struct InvWarpArgs {
+  long long batch, npts, ntiles;  // tiles of INV_WPTS points per profile
+  const double* o;
+  const double* theta;
+  double* D;
+  double* sorp;
+  int* status;
+  double* slope;
+  double* anti;
+  double* agg;    // [batch][ntiles][INV_NAGG]
+  double* gtot;   // [batch][ngroups][INV_NAGG], full groups only
+  double* stot;   // [batch][nsuper][INV_NAGG], full supergroups only
+  long long ngroups, nsuper;
+  int* gcount;    // [batch][ngroups] arrivals
+  int* scount;    // [batch][nsuper] closed groups
+  unsigned long long* ticket;
+};
+
+template <int NC>
+__device__ __forceinline__ void look_back3(const InvWarpArgs& A, long long p, long long t, unsigned lane,
+                                           double (&part)[NC]) {
+  const long long G = t / INV_GROUP, S = G / INV_GROUP;
+  const long long k = G * INV_GROUP + lane, g = S * INV_GROUP + lane;
+  const double* sa = A.agg + (p * A.ntiles + k) * INV_NAGG;
+  const double* sg = A.gtot + (p * A.ngroups + g) * INV_NAGG;
+  const double* ss = A.stot + (p * A.nsuper + lane) * INV_NAGG;
+  const bool need_a = k < t, need_g = g < G, need_s = (long long)lane < S;
+  double va[NC], vg[NC], vs[NC];
+#pragma unroll
+  for (int c = 0; c < NC; c++) {  // all three levels requested at once
+    vs[c] = need_s ? __ldcg(ss + c) : 0.0;
+    vg[c] = need_g ? __ldcg(sg + c) : 0.0;
+    va[c] = need_a ? __ldcg(sa + c) : 0.0;
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    if (is_unset(vs[c])) vs[c] = wait_load1(ss + c);
+    part[c] = vs[c];
+  }
+  for (long long si = lane + 32; si < S; si += 32) {  // profiles beyond 32 supergroups (2.7e8 points)
+    const double* src = A.stot + (p * A.nsuper + si) * INV_NAGG;
+#pragma unroll
+    for (int c = 0; c < NC; c++) part[c] += wait_load1(src + c);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) {
+    if (is_unset(vg[c])) vg[c] = wait_load1(sg + c);
+    part[c] += vg[c];
+    if (is_unset(va[c])) va[c] = wait_load1(sa + c);
+    part[c] += va[c];
+  }
+#pragma unroll
+  for (int c = 0; c < NC; c++) part[c] = warp_sum(part[c]);
+}
+
+template <bool SORP, bool A16>
+__global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_warp_kernel(const InvWarpArgs A) {
+  __shared__ double2 s_in[2][INV_NW][INV_WCHP + 2];  // the next tile's (theta, o), each warp's own points
+  extern __shared__ double2 s_dyn[];  // [INV_DEFER][2][INV_NW][INV_WCH]: slopes and in-tile prefixes of the deferred tiles
+
+  const int tid = threadIdx.x;
+  const unsigned lane = tid & 31, wid = tid >> 5;
+  auto s_dd = [&](int slot) { return s_dyn + ((size_t)(slot * 2 + 0) * INV_NW + wid) * INV_WCH; };
+  auto s_ee = [&](int slot) { return s_dyn + ((size_t)(slot * 2 + 1) * INV_NW + wid) * INV_WCH; };
+  const long long total_tiles = A.batch * A.ntiles;
+  const long long n = A.npts;
+  auto bulk_tile = [&](long long t) {  // the points up to r0+256+1 exist, r0+256 is not the last
+    const long long r0 = t * INV_WPTS;
+    return r0 + INV_WPTS + 2 <= n && n > 2;
+  };
+  // Lane 0 takes the ticket with a bare atom (atomicAdd's warp-aggregated form waits for the answer on
+  // the spot); nothing touches the answer until the tile in hand is done, then every lane decodes it.
+  auto take_ticket = [&]() {
+    unsigned long long tk = 0;
+    if (lane == 0) asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(tk) : "l"(A.ticket) : "memory");
+    return tk;
+  };
+  long long p = 0, t = 0;
+  auto decode_ticket = [&](unsigned long long raw) {
+    const long long tk = (long long)__shfl_sync(0xffffffffu, raw, 0);
+    p = tk < total_tiles ? tk / A.ntiles : A.batch;
+    t = tk - p * A.ntiles;
+  };
+  decode_ticket(take_ticket());
+  bool have = p < A.batch;
+  double dir_a = 0.0, dir_b = 0.0;
+  auto request_tile = [&]() {
+    const long long wbase = n - t * INV_WPTS - INV_WPTS;
+    const double* th_g = A.theta + p * n;
+    const double* o_g = A.o + p * n;
+    dir_a = th_g[n - 2];
+    dir_b = th_g[n - 1];
+    if (bulk_tile(t)) {
+      request_warp<false, A16>(th_g, n, wbase, s_in[0][wid], lane);
+      request_warp<false, A16>(o_g, n, wbase, s_in[1][wid], lane);
+    } else {
+      request_warp<true, false>(th_g, n, wbase, s_in[0][wid], lane);
+      request_warp<true, false>(o_g, n, wbase, s_in[1][wid], lane);
+    }
+  };
+  if (have) request_tile();
+
+  long long pv_p[INV_DEFER], pv_t[INV_DEFER];
+#pragma unroll
+  for (int q = 0; q < INV_DEFER; q++) pv_p[q] = -1, pv_t[q] = 0;
+  int slot = 0;
+
+  for (;;) {
+    if (!have && pv_p[0] < 0 && pv_p[INV_DEFER - 1] < 0) break;
+    unsigned long long next_raw = ~0ull >> 1;  // "none left"
+    if (have) next_raw = take_ticket();  // one tile ahead; looked at only after this tile's arithmetic
+    double d[INV_ITEMS + 1], excl[INV_ITEMS];
+    int arrived = 0;
+    if (have) {
+      const long long rb = t * INV_WPTS + (long long)lane * INV_ITEMS;
+      const double* th_g = A.theta + p * n;
+      const double* o_g = A.o + p * n;
+      const double dir_step = dir_a - dir_b;
+      double x[INV_NP], y[INV_NP];
+      cp_async_wait_all();
+      __syncwarp();
+      collect_chunk(s_in[0][wid], lane, x);
+      collect_chunk(s_in[1][wid], lane, y);
+      double I[INV_ITEMS], sumF, sumT;
+      bool mono;
+      const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);
+      if (bulk_tile(t)) compute_chunk<false, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
+      else compute_chunk<true, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
+      const bool anybad = __any_sync(0xffffffffu, flat || !mono);
+
+      double run = 0.0;
+#pragma unroll
+      for (int j = 0; j < INV_ITEMS; j++) {
+        excl[j] = run;
+        run += I[j];
+      }
+      const double wincl = warp_incl_scan(run, lane);
+      const double toff = wincl - run;
+#pragma unroll
+      for (int j = 0; j < INV_ITEMS; j++) excl[j] += toff;
+      const double carry = __shfl_sync(0xffffffffu, wincl, 31);
+      double f = 0.0, z = 0.0;
+      if (SORP) {
+        f = warp_sum(sumF);  // the two sorptivity integrands (fixed tree)
+        z = warp_sum(sumT);
+      }
+      // ---- publish; the last tile of a group (supergroup) closes it ---------------------------------
+      if (lane == 0) {
+        double* ag = A.agg + (p * A.ntiles + t) * INV_NAGG;
+        __stcg(ag + 0, carry);
+        __stcg(ag + 1, f);
+        __stcg(ag + 2, z);
+        __stcg(ag + 3, anybad ? 1.0 : 0.0);
+      }
+      // whoever arrives last in a full group closes it (nobody ever waits for a particular tile here);
+      // the count comes back while the next tile is being requested
+      if (lane == 0 && t / INV_GROUP < A.ngroups) arrived = atomicAdd(A.gcount + p * A.ngroups + t / INV_GROUP, 1);
+    }
+
+    // ---- the points of the next tile are requested before anything else is waited for ---------------
+    const long long this_p = p, this_t = t;
+    const bool had = have;
+    decode_ticket(next_raw);
+    have = p < A.batch;
+    if (have) request_tile();
+
+    // ---- close the group, and the supergroup, if this warp's tile was the last of it to arrive --------
+    arrived = __shfl_sync(0xffffffffu, arrived, 0);
+    if (had && arrived == INV_GROUP - 1) {
+      const long long G = this_t / INV_GROUP;
+      double tot[INV_NAGG];
+      wait_load4(A.agg + (this_p * A.ntiles + G * INV_GROUP + lane) * INV_NAGG, tot);
+#pragma unroll
+      for (int c = 0; c < INV_NAGG; c++) tot[c] = warp_sum(tot[c]);
+      int arrived2 = 0;
+      if (lane == 0) {
+        double* gt = A.gtot + (this_p * A.ngroups + G) * INV_NAGG;
+#pragma unroll
+        for (int c = 0; c < INV_NAGG; c++) __stcg(gt + c, tot[c]);
+        if (G / INV_GROUP < A.nsuper) arrived2 = atomicAdd(A.scount + this_p * A.nsuper + G / INV_GROUP, 1);
+      }
+      arrived2 = __shfl_sync(0xffffffffu, arrived2, 0);
+      if (arrived2 == INV_GROUP - 1) {
+        const long long S = G / INV_GROUP;
+        wait_load4(A.gtot + (this_p * A.ngroups + S * INV_GROUP + lane) * INV_NAGG, tot);
+#pragma unroll
+        for (int c = 0; c < INV_NAGG; c++) tot[c] = warp_sum(tot[c]);
+        if (lane == 0) {
+          double* st = A.stot + (this_p * A.nsuper + S) * INV_NAGG;
+#pragma unroll
+          for (int c = 0; c < INV_NAGG; c++) __stcg(st + c, tot[c]);
+        }
+      }
+    }
+
+    // ---- the deferred tile -----------------------------------------------------------------------------
+    if (pv_p[0] >= 0) {
+      const long long p2 = pv_p[0], t2 = pv_t[0];
+      const bool closes = (t2 == A.ntiles - 1);  // the last tile of a profile closes its sums
+      double prefix, tot[INV_NAGG];
+      if (closes) {
+        look_back3<INV_NAGG>(A, p2, t2, lane, tot);
+        prefix = tot[0];
+      } else {
+        double one[1];
+        look_back3<1>(A, p2, t2, lane, one);
+        prefix = one[0];
+      }
+      const long long wb2 = n - t2 * INV_WPTS - INV_WPTS;  // may be < 0 in the last tile
+      __syncwarp();
+      const int xl = ((int)lane & ~7) | (((int)lane & 7) ^ (((int)lane >> 3) & 3));
+      const double2* sd = s_dd(slot) + xl;
+      const double2* se = s_ee(slot) + xl;
+      const long long at0 = p2 * n + wb2 + 2 * (long long)lane;
+      if (A16 && wb2 >= 0 && !A.slope && !A.anti) {
+        double2* Dp = reinterpret_cast<double2*>(A.D + at0);
+#pragma unroll
+        for (int q = 0; q < INV_CH; q++) {
+          const double2 dd = sd[q * 32], ee = se[q * 32];
+          Dp[32 * q] = make_double2(-(dd.x * (prefix + ee.x)) * 0.5, -(dd.y * (prefix + ee.y)) * 0.5);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < INV_CH; q++) {
+          const long long mi = wb2 + 2 * (32 * q + (long long)lane);
+          const double2 dd = sd[q * 32], ee = se[q * 32];
+          const double ix = prefix + ee.x, iy = prefix + ee.y;
+          const double2 Dv = make_double2(-(dd.x * ix) * 0.5, -(dd.y * iy) * 0.5);
+          const long long at = at0 + 64 * q;
+          if (A16) {
+            if (mi >= 0) *reinterpret_cast<double2*>(A.D + at) = Dv;
+          } else {
+            if (mi >= 0) A.D[at] = Dv.x;
+            if (mi + 1 >= 0) A.D[at + 1] = Dv.y;
+          }
+          if (A.slope) {
+            if (mi >= 0) A.slope[at] = dd.x;
+            if (mi + 1 >= 0) A.slope[at + 1] = dd.y;
+          }
+          if (A.anti) {
+            if (mi >= 0) A.anti[at] = ix;
+            if (mi + 1 >= 0) A.anti[at + 1] = iy;
+          }
+        }
+      }
+      if (closes && lane == 0) {
+        const double* th_g = A.theta + p2 * n;
+        const double* o_g = A.o + p2 * n;
+        const double* own = A.agg + (p2 * A.ntiles + t2) * INV_NAGG;
+        const double nbad = tot[3] + __ldcg(own + 3);
+        A.status[p2] = (nbad != 0.0) ? 1 : 0;
+        if (SORP) {
+          double F = tot[1] + __ldcg(own + 1), Z = tot[2] + __ldcg(own + 2);
+          double* out = A.sorp + p2 * 4;
+          out[0] = -F;  // traversal runs from o_last down to o_first: Int_{o_first}^{o_last} theta do = -sum
+          out[1] = -Z;
+          out[2] = pchip_extrapolated_head(o_g, th_g, n);
+          out[3] = 0.0;
+        }
+      }
+    }
+
+    if (had) {
+      __syncwarp();  // the lanes' reads of the deferred tile above come before these writes
+#pragma unroll
+      for (int i = 0; i < INV_CH; i++) {  // chunk 4u + i holds the thread's points j = 7-2i, 6-2i
+        const int u = 31 - (int)lane;
+        const int c = INV_CH * u + (i ^ ((u >> 1) & 3));
+        s_dd(slot)[c] = make_double2(d[INV_ITEMS - 1 - 2 * i], d[INV_ITEMS - 2 - 2 * i]);
+        s_ee(slot)[c] = make_double2(excl[INV_ITEMS - 1 - 2 * i], excl[INV_ITEMS - 2 - 2 * i]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q + 1 < INV_DEFER; q++) pv_p[q] = pv_p[q + 1], pv_t[q] = pv_t[q + 1];
+    pv_p[INV_DEFER - 1] = had ? this_p : -1;
+    pv_t[INV_DEFER - 1] = this_t;
+    slot = (slot + 1 == INV_DEFER) ? 0 : slot + 1;
   }
 }
 
@@ -749,10 +1040,71 @@ __global__ void pchip_eval_kernel(long long batch, long long n, const double* __
   }
 }
 
+inline cudaError_t inverse_launch_warp(long long batch, long long npts, const double* o, const double* theta,
+                                       double* D, double* sorp, int* status, double* slope, double* anti,
+                                       int sms, cudaStream_t s, int* launches) {
+  InvWarpArgs a;
+  a.batch = batch;
+  a.npts = npts;
+  a.ntiles = (npts + INV_WPTS - 1) / INV_WPTS;
+  a.o = o;
+  a.theta = theta;
+  a.D = D;
+  a.sorp = sorp;
+  a.status = status;
+  a.slope = slope;
+  a.anti = anti;
+  a.ngroups = a.ntiles / INV_GROUP;   // full groups
+  a.nsuper = a.ngroups / INV_GROUP;   // full supergroups
+  const size_t tiles = (size_t)batch * (size_t)a.ntiles;
+  const size_t entries = tiles + (size_t)batch * (size_t)(a.ngroups + a.nsuper) + 1;
+  const size_t agg_bytes = entries * INV_NAGG * sizeof(double);
+  const size_t cnt_bytes = ((size_t)batch * (size_t)(a.ngroups + a.nsuper) * sizeof(int) + 15) / 8 * 8;
+  char* scratch = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&scratch, agg_bytes + cnt_bytes + 64, s);
+  if (e != cudaSuccess) return e;
+  a.agg = reinterpret_cast<double*>(scratch);
+  a.gtot = a.agg + tiles * INV_NAGG;
+  a.stot = a.gtot + (size_t)batch * (size_t)a.ngroups * INV_NAGG;
+  a.gcount = reinterpret_cast<int*>(scratch + agg_bytes);
+  a.scount = a.gcount + (size_t)batch * (size_t)a.ngroups;
+  a.ticket = reinterpret_cast<unsigned long long*>(scratch + agg_bytes + cnt_bytes);
+  e = cudaMemsetAsync(scratch, 0xff, agg_bytes, s);  // the "unset" pattern (see is_unset)
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(scratch + agg_bytes, 0, cnt_bytes + 64, s);
+  if (e != cudaSuccess) return e;
+  const bool a16 = (npts % 2 == 0) && ((((uintptr_t)o | (uintptr_t)theta | (uintptr_t)D) & 15) == 0);
+  void (*kern)(const InvWarpArgs) =
+      sorp ? (a16 ? inverse_scan_warp_kernel<true, true> : inverse_scan_warp_kernel<true, false>)
+           : (a16 ? inverse_scan_warp_kernel<false, true> : inverse_scan_warp_kernel<false, false>);
+  const size_t dyn = (size_t)INV_DEFER * 2 * INV_NW * INV_WCH * sizeof(double2);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  int bps = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, INV_BLOCK, dyn);
+  if (e != cudaSuccess) return e;
+  if (bps < 1) bps = 1;
+  const long long cap = (long long)sms * bps;
+  const long long want = ((long long)tiles + INV_NW - 1) / INV_NW;
+  int grid = (int)(want < cap ? want : cap);
+  if (grid < 1) grid = 1;
+  kern<<<grid, INV_BLOCK, dyn, s>>>(a);
+  *launches = 1;
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  return cudaFreeAsync(scratch, s);
+}
+
 inline cudaError_t inverse_launch(long long batch, long long npts, const double* o,
                                   const double* theta, double* D, double* sorp, int* status,
                                   double* slope, double* anti,
                                   int sms, cudaStream_t s, int* launches) {
+  {
+    const char* k = getenv("FX_INV_KERNEL");
+    if (k && atoi(k) == 1) return inverse_launch_warp(batch, npts, o, theta, D, sorp, status, slope, anti, sms, s, launches);
+  }
   InvArgs a;
   a.batch = batch;
   a.npts = npts;
