@@ -16,18 +16,22 @@
 // decreasing profile and its exact mirror for an increasing one.
 //
 // Algorithmic traffic: 16 B/point read (o, theta), 8 B/point written (D); every point is
-// read once (plus a 3-point halo per warp), measured DRAM traffic equals it.  One CTA owns a tile of
-// INV_TILE consecutive points of one profile, one WARP 256 of them, one THREAD a chunk of INV_ITEMS
-// consecutive points, which it keeps in registers:
+// read once (plus a 3-point halo per warp), measured DRAM traffic equals it.
+//
+// Every WARP is on its own (there is no CTA barrier in the kernel): it takes tickets, in order, for
+// tiles of 256 consecutive points of one profile, each THREAD owning INV_ITEMS = 8 consecutive points
+// that it keeps in registers:
 //   the warp stages its points with coalesced cp.async, a tile ahead (request_warp / collect_chunk)
 //   steps (d theta, d o) of the chunk's intervals and the two either side
 //   PCHIP slope do/dtheta at the chunk's points (and dtheta/do when the sorptivity is wanted)
-//   per-interval cubic-Hermite integrals; running sum in the thread, one warp scan of the thread
-//   totals, the four warp totals through shared memory (the tile's only barrier)
-//   publish the tile aggregate, go on to the next two tiles, then add up the aggregates of all
-//   EARLIER tiles of the profile in a fixed two-level order (tickets are handed out in order,
-//   so every earlier tile is resident or finished: no deadlock, no serial chain, and the
-//   result is bit-reproducible run to run)
+//   per-interval cubic-Hermite integrals; running sum in the thread, one warp scan of the thread totals
+//   publish the tile aggregate; whoever ARRIVES last in a group of 32 tiles publishes the group total,
+//   whoever closes the last group of a supergroup of 32 groups the supergroup total
+//   go on to the next two tiles, then add up what lies before the tile in its profile in a fixed
+//   three-level order: earlier supergroup totals, earlier group totals of its supergroup, earlier
+//   aggregates of its group (tickets are handed out in order, so every earlier tile is held by a
+//   warp that publishes before it waits for anything: no deadlock, no serial chain, and the
+//   association depends on the tile index alone: bit-reproducible run to run)
 //   D = -d * (prefix + local)/2, written coalesced in the caller's point order.
 //
 // Arithmetic: an fp64 division costs ~25 issue slots on sm_100a (scripts/ubench_fp64.cu), and
@@ -36,6 +40,11 @@
 // striped shared-memory tile, 4 reciprocals per point) reached 21 % at 363 instructions per point.
 // Here the harmonic mean is cleared of its divisions algebraically (pchip_interior_steps): ONE
 // reciprocal per point and slope, no secant formed, no shuffle outside the scan.
+//
+// The kernel is a latency chain -- publish -> group total -> look-back -> next publish -- and every
+// choice below that looks odd was measured on C5 (10^3 profiles x 10^6 points); DESIGN.md 3.4 has the
+// list.  The CTA-tiled form of the same kernel (1024-point tiles, one barrier per tile, two-level
+// look-back) ran at 6.2 ms where this one runs at 5.7 ms.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -49,8 +58,7 @@ namespace fx {
 
 constexpr int INV_BLOCK = 128;
 constexpr int INV_ITEMS = 8;                      // consecutive points owned by one thread
-constexpr int INV_TILE = INV_BLOCK * INV_ITEMS;   // 1024 points per tile
-constexpr int INV_NW = INV_BLOCK / 32;
+constexpr int INV_NW = INV_BLOCK / 32;            // independent warps per CTA
 constexpr int INV_NAGG = 4;  // inverse integral, forward PCHIP integral, trapezoid, flagged-bad count
 constexpr int INV_GROUP = 32; // tiles per look-back group (one warp reads a group)
 #ifndef FX_INV_CTAS
@@ -66,22 +74,6 @@ constexpr int INV_GROUP = 32; // tiles per look-back group (one warp reads a gro
 #define FX_INV_DEFER 2
 #endif
 constexpr int INV_DEFER = FX_INV_DEFER;  // a tile's output is written this many tiles later
-
-struct InvArgs {
-  long long batch, npts, ntiles;      // tiles per profile
-  const double* o;                    // [batch][npts]
-  const double* theta;                // [batch][npts]
-  double* D;                          // [batch][npts]
-  double* sorp;                       // [batch][4]: PCHIP Int theta do, trapezoid Int theta do, extrapolated Int_0^o0, spare; or nullptr
-  int* status;                        // [batch]
-  double* slope;                      // [batch][npts] do/dtheta at the knots, or nullptr
-  double* anti;                       // [batch][npts] Int_i^theta o dtheta at the knots, or nullptr
-  double* agg;                        // [batch][ntiles][INV_NAGG] tile aggregates
-  double* gtot;                       // [batch][ngroups][INV_NAGG] totals of the full groups of INV_GROUP tiles
-  int* gcount;                        // [batch][ngroups] tiles of the group that have published
-  long long ngroups;                  // ceil(ntiles / INV_GROUP)
-  unsigned long long* ticket;
-};
 
 __device__ __forceinline__ double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 
@@ -347,45 +339,6 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, c
   }
 }
 
-// Sum over the tiles before tile t of profile p of the first NC components of their aggregates, by
-// one warp, every lane returning the same value.  Two fixed levels, no chain: whoever publishes the
-// last aggregate of a group of INV_GROUP tiles also publishes the group total; a tile adds the totals
-// of all earlier groups and the aggregates of its own group's earlier tiles.
-// O(ntiles/INV_GROUP + INV_GROUP) reads and -- the association being fixed by the tile index
-// alone -- bit-reproducible run to run, and the same in every warp that asks.
-template <int NC>
-__device__ __forceinline__ void look_back(const InvArgs& A, long long p, long long t, unsigned lane,
-                                          double (&part)[NC]) {
-  const long long g = t / INV_GROUP, k = g * INV_GROUP + lane;
-  const double* sg = A.gtot + (p * A.ngroups + lane) * INV_NAGG;
-  const double* sa = A.agg + (p * A.ntiles + k) * INV_NAGG;
-  const bool need_g = (long long)lane < g, need_a = k < t;
-  // both levels requested at once: one L2 round trip when everything is there, as it usually is
-  double vg[NC], va[NC];
-#pragma unroll
-  for (int c = 0; c < NC; c++) {
-    vg[c] = need_g ? __ldcg(sg + c) : 0.0;
-    va[c] = need_a ? __ldcg(sa + c) : 0.0;
-  }
-#pragma unroll
-  for (int c = 0; c < NC; c++) {
-    if (is_unset(vg[c])) vg[c] = wait_load1(sg + c);
-    part[c] = vg[c];
-  }
-  for (long long gi = lane + 32; gi < g; gi += 32) {  // profiles beyond 32 groups (33 M points)
-    const double* src = A.gtot + (p * A.ngroups + gi) * INV_NAGG;
-#pragma unroll
-    for (int c = 0; c < NC; c++) part[c] += wait_load1(src + c);
-  }
-#pragma unroll
-  for (int c = 0; c < NC; c++) {
-    if (is_unset(va[c])) va[c] = wait_load1(sa + c);
-    part[c] += va[c];
-  }
-#pragma unroll
-  for (int c = 0; c < NC; c++) part[c] = warp_sum(part[c]);
-}
-
 // Int_0^{o_first} of the forward PCHIP's first cubic extrapolated back to o = 0 (scipy extrapolate=True)
 __device__ __forceinline__ double pchip_extrapolated_head(const double* o_g, const double* th_g, long long n) {
   double ext = 0.0;
@@ -411,265 +364,12 @@ __device__ __forceinline__ double pchip_extrapolated_head(const double* o_g, con
   return ext;
 }
 
-template <bool SORP, bool A16>
-__global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(const InvArgs A) {
-  __shared__ double2 s_in[2][INV_NW][INV_WCHP + 2];  // the next tile's (theta, o), each warp's own points
-  // A tile's output is written one tile later (see below): its slopes and in-tile prefixes wait here,
-  // in the same chunk layout, each warp's own.
-  __shared__ double s_wt[2][INV_NW];
-  __shared__ double s_warp[2][2][INV_NW];
-  __shared__ unsigned long long s_tick[2];
-
-  const int tid = threadIdx.x;
-  const unsigned lane = tid & 31, wid = tid >> 5;
-  extern __shared__ double2 s_dyn[];  // [INV_DEFER][2][INV_NW][INV_WCH]: slopes and in-tile prefixes of the deferred tiles
-  auto s_dd = [&](int slot) { return s_dyn + ((size_t)(slot * 2 + 0) * INV_NW + wid) * INV_WCH; };
-  auto s_ee = [&](int slot) { return s_dyn + ((size_t)(slot * 2 + 1) * INV_NW + wid) * INV_WCH; };
-  const long long total_tiles = A.batch * A.ntiles;
-  const long long n = A.npts;
-
-  // The prefix of a tile needs the aggregates of every earlier tile of its profile, which other
-  // CTAs are computing at the same moment: waiting for them right away left 45 % of the warp
-  // time there.  So a tile publishes its aggregate, the CTA requests the points of its NEXT tile
-  // (cp.async), and only then each warp resolves the previous tile's prefix and writes its output.
-  // Tickets are taken one tile ahead (so the requests can be) and in order; aggregates are published
-  // before anything is waited for and a blocked CTA only ever holds unpublished tiles LATER than
-  // the one it waits on, so the waits cannot form a cycle.
-  auto bulk_tile = [&](long long t) {  // the points up to r0+TILE+1 exist, r0+TILE is not the last
-    const long long r0 = t * INV_TILE;
-    return r0 + INV_TILE + 2 <= n && n > 2;
-  };
-
-  if (tid == 0) s_tick[0] = atomicAdd(A.ticket, 1ull);
-  __syncthreads();
-  long long ticket = (long long)s_tick[0];
-  bool have = ticket < total_tiles;
-  long long p = 0, t = 0;
-  double dir_a = 0.0, dir_b = 0.0;  // the profile's first traversal step tells its direction
-  auto request_tile = [&]() {
-    p = ticket / A.ntiles;
-    t = ticket - p * A.ntiles;
-    const long long wbase = n - t * INV_TILE - (long long)INV_WPTS * (wid + 1);
-    const double* th_g = A.theta + p * n;
-    const double* o_g = A.o + p * n;
-    dir_a = th_g[n - 2];
-    dir_b = th_g[n - 1];
-    if (bulk_tile(t)) {
-      request_warp<false, A16>(th_g, n, wbase, s_in[0][wid], lane);
-      request_warp<false, A16>(o_g, n, wbase, s_in[1][wid], lane);
-    } else {
-      request_warp<true, false>(th_g, n, wbase, s_in[0][wid], lane);
-      request_warp<true, false>(o_g, n, wbase, s_in[1][wid], lane);
-    }
-  };
-  if (have) request_tile();
-
-  // the deferred tiles, oldest first; tile number k of this CTA keeps its data in slot k % INV_DEFER
-  long long pv_p[INV_DEFER], pv_t[INV_DEFER];
-#pragma unroll
-  for (int q = 0; q < INV_DEFER; q++) pv_p[q] = -1, pv_t[q] = 0;
-  int slot = 0;
-  int par = 0;
-
-  for (;;) {
-    if (!have && pv_p[0] < 0 && pv_p[INV_DEFER - 1] < 0) break;
-    if (tid == 0 && have) s_tick[par ^ 1] = atomicAdd(A.ticket, 1ull);
-    double d[INV_ITEMS + 1], excl[INV_ITEMS];
-    double run = 0.0, wincl = 0.0;
-    bool bad = false;
-    if (have) {
-      const long long rb = t * INV_TILE + (long long)tid * INV_ITEMS;
-      const double* th_g = A.theta + p * n;
-      const double* o_g = A.o + p * n;
-      const double dir_step = dir_a - dir_b;
-      double x[INV_NP], y[INV_NP];
-      cp_async_wait_all();
-      __syncwarp();
-      collect_chunk(s_in[0][wid], lane, x);
-      collect_chunk(s_in[1][wid], lane, y);
-      double I[INV_ITEMS], sumF, sumT;
-      bool mono;
-      const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);
-      if (bulk_tile(t)) compute_chunk<false, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
-      else compute_chunk<true, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
-      bad = flat || !mono;
-
-      // in-thread running sums, then one warp scan of the thread totals
-#pragma unroll
-      for (int j = 0; j < INV_ITEMS; j++) {
-        excl[j] = run;
-        run += I[j];
-      }
-      wincl = warp_incl_scan(run, lane);
-      if (lane == 31) s_wt[par][wid] = wincl;
-      if (SORP) {
-        sumF = warp_sum(sumF);  // the two sorptivity integrands (fixed tree)
-        sumT = warp_sum(sumT);
-        if (lane == 0) {
-          s_warp[par][0][wid] = sumF;
-          s_warp[par][1][wid] = sumT;
-        }
-      }
-    }
-    const int anybad = __syncthreads_or(bad ? 1 : 0);  // the one barrier of a tile
-    const long long next_ticket = have ? (long long)s_tick[par ^ 1] : total_tiles;
-
-    // ---- the points of the next tile are requested before anything is waited for --------------------
-    const long long this_p = p, this_t = t;
-    const bool had = have;
-    ticket = next_ticket;
-    have = ticket < total_tiles;
-    if (have) request_tile();
-
-    if (had) {
-      double woff = 0.0, carry = 0.0;  // fixed order: bit-reproducible
-#pragma unroll
-      for (int w = 0; w < INV_NW; w++) {
-        const double v = s_wt[par][w];
-        if (w < (int)wid) woff += v;
-        carry += v;
-      }
-      const double toff = woff + (wincl - run);
-#pragma unroll
-      for (int j = 0; j < INV_ITEMS; j++) excl[j] += toff;
-
-      // ---- publish the tile aggregate; close the group if this is its last tile to arrive ------
-      if (wid == 0) {
-        if (lane == 0) {
-          double f = 0.0, z = 0.0;
-          if (SORP) {
-            for (int w = 0; w < INV_NW; w++) {
-              f += s_warp[par][0][w];
-              z += s_warp[par][1][w];
-            }
-          }
-          double* ag = A.agg + (this_p * A.ntiles + this_t) * INV_NAGG;
-          __stcg(ag + 0, carry);
-          __stcg(ag + 1, f);
-          __stcg(ag + 2, z);
-          __stcg(ag + 3, (double)anybad);
-        }
-        // the arrival count only elects who closes the group; the closer waits for the VALUES (wait_load4),
-        // so no fence is needed between the stores above and the count
-        const long long g = this_t / INV_GROUP, g0 = g * INV_GROUP;
-        const bool full = g < A.ntiles / INV_GROUP;
-        int arrived = 0;
-        if (lane == 0 && full) arrived = atomicAdd(A.gcount + this_p * A.ngroups + g, 1);
-        arrived = __shfl_sync(0xffffffffu, arrived, 0);
-        if (full && arrived == INV_GROUP - 1) {
-          double tot[INV_NAGG];
-          wait_load4(A.agg + (this_p * A.ntiles + g0 + lane) * INV_NAGG, tot);
-#pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) tot[c] = warp_sum(tot[c]);
-          if (lane == 0) {
-            double* gt = A.gtot + (this_p * A.ngroups + g) * INV_NAGG;
-#pragma unroll
-            for (int c = 0; c < INV_NAGG; c++) __stcg(gt + c, tot[c]);
-          }
-        }
-      }
-    }
-
-    // ---- the deferred tile: every warp sums the earlier tiles of its profile, then writes its output --
-    if (pv_p[0] >= 0) {
-      const long long p2 = pv_p[0], t2 = pv_t[0];
-      const bool closes = (t2 == A.ntiles - 1) && wid == 0;  // the last tile of a profile closes its sums
-      double prefix, tot[INV_NAGG];
-      if (closes) {
-        look_back<INV_NAGG>(A, p2, t2, lane, tot);
-        prefix = tot[0];
-      } else {
-        double one[1];
-        look_back<1>(A, p2, t2, lane, one);
-        prefix = one[0];
-      }
-      // D in the caller's order, whole sectors per instruction: lane l takes chunk 32 q + l of the warp's
-      // run (whichever thread computed its slopes), memory indices wb2 + 2c and wb2 + 2c + 1
-      const long long wb2 = n - t2 * INV_TILE - (long long)INV_WPTS * (wid + 1);  // may be < 0 in the last tile
-      __syncwarp();
-      // the stash is XOR-swizzled within its 128-byte rows (no padding: two deferred tiles must fit):
-      // chunk 32 q + lane sits at 32 q + xl
-      const int xl = ((int)lane & ~7) | (((int)lane & 7) ^ (((int)lane >> 3) & 3));
-      const double2* sd = s_dd(slot) + xl;
-      const double2* se = s_ee(slot) + xl;
-      const long long at0 = p2 * n + wb2 + 2 * (long long)lane;  // chunk q of the lane starts at at0 + 64 q
-      if (A16 && wb2 >= 0 && !A.slope && !A.anti) {  // all but a profile's last tile: nothing to guard
-        double2* Dp = reinterpret_cast<double2*>(A.D + at0);
-#pragma unroll
-        for (int q = 0; q < INV_CH; q++) {
-          const double2 dd = sd[q * 32], ee = se[q * 32];
-          Dp[32 * q] = make_double2(-(dd.x * (prefix + ee.x)) * 0.5, -(dd.y * (prefix + ee.y)) * 0.5);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < INV_CH; q++) {
-          const long long mi = wb2 + 2 * (32 * q + (long long)lane);
-          const double2 dd = sd[q * 32], ee = se[q * 32];
-          const double ix = prefix + ee.x, iy = prefix + ee.y;
-          const double2 Dv = make_double2(-(dd.x * ix) * 0.5, -(dd.y * iy) * 0.5);
-          const long long at = at0 + 64 * q;
-          if (A16) {
-            if (mi >= 0) *reinterpret_cast<double2*>(A.D + at) = Dv;
-          } else {
-            if (mi >= 0) A.D[at] = Dv.x;
-            if (mi + 1 >= 0) A.D[at + 1] = Dv.y;
-          }
-          if (A.slope) {
-            if (mi >= 0) A.slope[at] = dd.x;
-            if (mi + 1 >= 0) A.slope[at + 1] = dd.y;
-          }
-          if (A.anti) {
-            if (mi >= 0) A.anti[at] = ix;
-            if (mi + 1 >= 0) A.anti[at + 1] = iy;
-          }
-        }
-      }
-
-      if (closes && lane == 0) {
-        const double* th_g = A.theta + p2 * n;
-        const double* o_g = A.o + p2 * n;
-        const double* own = A.agg + (p2 * A.ntiles + t2) * INV_NAGG;
-        const double nbad = tot[3] + __ldcg(own + 3);
-        A.status[p2] = (nbad != 0.0) ? 1 : 0;
-        if (SORP) {
-          double F = tot[1] + __ldcg(own + 1), Z = tot[2] + __ldcg(own + 2);
-          // traversal runs from o_last down to o_first: Int_{o_first}^{o_last} theta do = -sum
-          double* out = A.sorp + p2 * 4;
-          out[0] = -F;
-          out[1] = -Z;
-          out[2] = pchip_extrapolated_head(o_g, th_g, n);
-          out[3] = 0.0;
-        }
-      }
-    }
-
-    if (had) {
-      __syncwarp();  // the lanes' reads of the deferred tile above come before these writes
-#pragma unroll
-      for (int i = 0; i < INV_CH; i++) {  // chunk 4u + i holds the thread's points j = 7-2i, 6-2i
-        const int u = 31 - (int)lane;
-        const int c = INV_CH * u + (i ^ ((u >> 1) & 3));  // chunk 4u + i, XOR-swizzled: stays within the thread's four
-        s_dd(slot)[c] = make_double2(d[INV_ITEMS - 1 - 2 * i], d[INV_ITEMS - 2 - 2 * i]);
-        s_ee(slot)[c] = make_double2(excl[INV_ITEMS - 1 - 2 * i], excl[INV_ITEMS - 2 - 2 * i]);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q + 1 < INV_DEFER; q++) pv_p[q] = pv_p[q + 1], pv_t[q] = pv_t[q + 1];
-    pv_p[INV_DEFER - 1] = had ? this_p : -1;
-    pv_t[INV_DEFER - 1] = this_t;
-    slot = (slot + 1 == INV_DEFER) ? 0 : slot + 1;
-    par ^= 1;
-  }
-}
-
-// ---- the same scan with WARP-sized tiles: no CTA barrier at all ---------------------------------------
-// Every warp is on its own: it takes tickets for tiles of 256 points, stages, computes, publishes and
-// looks back by itself.  Four times as many tiles, so the look-back has three fixed levels: aggregates of
-// the earlier tiles of the group of 32, totals of the earlier groups of the supergroup of 32 groups, totals
-// of the earlier supergroups.  Whoever ARRIVES last in a group (supergroup) publishes its total.  (Letting
-// the tile that is last by index wait for the others was measured at 450 ms: it waits, in line, for tiles
-// that other warps hold as their NEXT ticket, and everything behind its own next ticket waits with it.)
-struct InvWarpArgs {
+// Three fixed look-back levels: aggregates of the earlier tiles of the group of 32, totals of the earlier
+// groups of the supergroup of 32 groups, totals of the earlier supergroups.  Whoever ARRIVES last in a
+// group (supergroup) publishes its total.  (Letting the tile that is last by index wait for the others was
+// measured at 450 ms: it waits, in line, for tiles that other warps hold as their NEXT ticket, and
+// everything behind its own next ticket waits with it.)
+struct InvArgs {
   long long batch, npts, ntiles;  // tiles of INV_WPTS points per profile
   const double* o;
   const double* theta;
@@ -688,7 +388,7 @@ struct InvWarpArgs {
 };
 
 template <int NC>
-__device__ __forceinline__ void look_back3(const InvWarpArgs& A, long long p, long long t, unsigned lane,
+__device__ __forceinline__ void look_back3(const InvArgs& A, long long p, long long t, unsigned lane,
                                            double (&part)[NC]) {
   const long long G = t / INV_GROUP, S = G / INV_GROUP;
   const long long k = G * INV_GROUP + lane, g = S * INV_GROUP + lane;
@@ -725,7 +425,7 @@ __device__ __forceinline__ void look_back3(const InvWarpArgs& A, long long p, lo
 }
 
 template <bool SORP, bool A16>
-__global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_warp_kernel(const InvWarpArgs A) {
+__global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(const InvArgs A) {
   __shared__ double2 s_in[2][INV_NW][INV_WCHP + 2];  // the next tile's (theta, o), each warp's own points
   extern __shared__ double2 s_dyn[];  // [INV_DEFER][2][INV_NW][INV_WCH]: slopes and in-tile prefixes of the deferred tiles
 
@@ -1040,10 +740,10 @@ __global__ void pchip_eval_kernel(long long batch, long long n, const double* __
   }
 }
 
-inline cudaError_t inverse_launch_warp(long long batch, long long npts, const double* o, const double* theta,
+inline cudaError_t inverse_launch(long long batch, long long npts, const double* o, const double* theta,
                                        double* D, double* sorp, int* status, double* slope, double* anti,
                                        int sms, cudaStream_t s, int* launches) {
-  InvWarpArgs a;
+  InvArgs a;
   a.batch = batch;
   a.npts = npts;
   a.ntiles = (npts + INV_WPTS - 1) / INV_WPTS;
@@ -1074,9 +774,9 @@ inline cudaError_t inverse_launch_warp(long long batch, long long npts, const do
   e = cudaMemsetAsync(scratch + agg_bytes, 0, cnt_bytes + 64, s);
   if (e != cudaSuccess) return e;
   const bool a16 = (npts % 2 == 0) && ((((uintptr_t)o | (uintptr_t)theta | (uintptr_t)D) & 15) == 0);
-  void (*kern)(const InvWarpArgs) =
-      sorp ? (a16 ? inverse_scan_warp_kernel<true, true> : inverse_scan_warp_kernel<true, false>)
-           : (a16 ? inverse_scan_warp_kernel<false, true> : inverse_scan_warp_kernel<false, false>);
+  void (*kern)(const InvArgs) =
+      sorp ? (a16 ? inverse_scan_kernel<true, true> : inverse_scan_kernel<true, false>)
+           : (a16 ? inverse_scan_kernel<false, true> : inverse_scan_kernel<false, false>);
   const size_t dyn = (size_t)INV_DEFER * 2 * INV_NW * INV_WCH * sizeof(double2);
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
   if (e != cudaSuccess) return e;
@@ -1089,70 +789,6 @@ inline cudaError_t inverse_launch_warp(long long batch, long long npts, const do
   const long long cap = (long long)sms * bps;
   const long long want = ((long long)tiles + INV_NW - 1) / INV_NW;
   int grid = (int)(want < cap ? want : cap);
-  if (grid < 1) grid = 1;
-  kern<<<grid, INV_BLOCK, dyn, s>>>(a);
-  *launches = 1;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  return cudaFreeAsync(scratch, s);
-}
-
-inline cudaError_t inverse_launch(long long batch, long long npts, const double* o,
-                                  const double* theta, double* D, double* sorp, int* status,
-                                  double* slope, double* anti,
-                                  int sms, cudaStream_t s, int* launches) {
-  {
-    const char* k = getenv("FX_INV_KERNEL");
-    if (k && atoi(k) == 1) return inverse_launch_warp(batch, npts, o, theta, D, sorp, status, slope, anti, sms, s, launches);
-  }
-  InvArgs a;
-  a.batch = batch;
-  a.npts = npts;
-  a.ntiles = (npts + INV_TILE - 1) / INV_TILE;
-  a.o = o;
-  a.theta = theta;
-  a.D = D;
-  a.sorp = sorp;
-  a.status = status;
-  a.slope = slope;
-  a.anti = anti;
-  size_t tiles = (size_t)batch * (size_t)a.ntiles;
-  a.ngroups = (a.ntiles + INV_GROUP - 1) / INV_GROUP;
-  size_t groups = (size_t)batch * (size_t)a.ngroups;
-  size_t agg_bytes = (tiles + groups) * INV_NAGG * sizeof(double);  // tile aggregates, then group totals
-  size_t cnt_bytes = (groups * sizeof(int) + 7) / 8 * 8;            // arrival counts of the groups
-  char* scratch = nullptr;
-  cudaError_t e = cudaMallocAsync((void**)&scratch, agg_bytes + cnt_bytes + 64, s);
-  if (e != cudaSuccess) return e;
-  a.agg = reinterpret_cast<double*>(scratch);
-  a.gtot = a.agg + tiles * INV_NAGG;
-  a.gcount = reinterpret_cast<int*>(scratch + agg_bytes);
-  a.ticket = reinterpret_cast<unsigned long long*>(scratch + agg_bytes + cnt_bytes);
-  e = cudaMemsetAsync(scratch, 0xff, agg_bytes, s);  // the "unset" pattern (see is_unset)
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(scratch + agg_bytes, 0, cnt_bytes + 64, s);
-  if (e != cudaSuccess) return e;
-  // 16-byte loads and stores need every profile's chunks aligned: even npts and aligned arrays
-  const bool a16 = (npts % 2 == 0) && ((((uintptr_t)o | (uintptr_t)theta | (uintptr_t)D) & 15) == 0);
-  void (*kern)(const InvArgs) = sorp ? (a16 ? inverse_scan_kernel<true, true> : inverse_scan_kernel<true, false>)
-                                     : (a16 ? inverse_scan_kernel<false, true> : inverse_scan_kernel<false, false>);
-  const size_t dyn = (size_t)INV_DEFER * 2 * INV_NW * INV_WCH * sizeof(double2);
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  if (e != cudaSuccess) return e;
-  {
-    const char* co = getenv("FX_INV_CARVEOUT");
-    const int pct = co ? atoi(co) : 100;
-    if (pct >= 0) {
-      e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-      if (e != cudaSuccess) return e;
-    }
-  }
-  int bps = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, INV_BLOCK, dyn);
-  if (e != cudaSuccess) return e;
-  if (bps < 1) bps = 1;
-  long long cap = (long long)sms * bps;
-  int grid = (int)((long long)tiles < cap ? (long long)tiles : cap);
   if (grid < 1) grid = 1;
   kern<<<grid, INV_BLOCK, dyn, s>>>(a);
   *launches = 1;
