@@ -64,6 +64,8 @@ constexpr int INV_GROUP = 32; // tiles per look-back group (one warp reads a gro
 #ifndef FX_INV_CTAS
 #define FX_INV_CTAS 4  // resident CTAs per SM the register budget is set for
 #endif
+// compute_chunk: how many of a thread's nine slope steps may be in flight at once (D alone / with the
+// sorptivity sums, which carry two slopes per step); measured flat between 1 and 9 on C5
 #ifndef FX_INV_LAG
 #define FX_INV_LAG 3
 #endif
