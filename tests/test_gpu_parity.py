@@ -552,6 +552,33 @@ def test_inverse_many_long_profiles_reproducible_and_equal_to_single(fxo):
         assert float(first._sorp[j, 1]) == pytest.approx(s_trapz, rel=1e-12)
 
 
+def test_two_streams_at_once_inverse_and_solve():
+    """Both persistent kernels wait on other CTAs' results (aggregates of earlier tiles; the shot queue).
+    Tickets go only to CTAs that are running, so two launches sharing the SMs from two streams must both
+    finish, with the results they give alone."""
+    import torch
+
+    rng = np.random.default_rng(21)
+    a = rng.uniform(0.5, 2.0, 64)
+    o = np.linspace(0, 20, 200_000)[None, :] / a[:, None]
+    th = np.exp(-a[:, None] * o)
+    alone_inv = fx.inverse(o, th).D_at_knots.cpu().numpy()
+    models = vg_sweep(30_000, seed=9)
+    alone = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=0, throw=False).summary.cpu().numpy()
+    s1, s2, s3 = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        r1 = fx.inverse(o, th, throw=False)
+    with torch.cuda.stream(s2):
+        r2 = fx.inverse(o, th, throw=False)
+    with torch.cuda.stream(s3):
+        r3 = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(r1.D_at_knots.cpu().numpy(), alone_inv)
+    np.testing.assert_array_equal(r2.D_at_knots.cpu().numpy(), alone_inv)
+    np.testing.assert_array_equal(r3.summary.cpu().numpy(), alone)
+
+
 def test_inverse_long_increasing_and_non_monotone_in_the_bulk(fxo):
     """Tiles away from a profile's ends take the unguarded path: an increasing profile, and one flat
     step deep inside a long profile, must come out as on the guarded path."""
