@@ -153,6 +153,47 @@ def ncu_pipe_utilisation(n: int):
     return out or None
 
 
+def inverse_c5_probe(dev, stream, batch: int = 1000, npts: int = 1_000_000, reps: int = 3):
+    """BASELINE config C5 (10^3 profiles x 10^6 points, theta = exp(-a o)): the profile -> D inverse scan,
+    inputs resident, CUDA events, against the HBM copy bandwidth (24 algorithmic bytes per point)."""
+    import torch
+
+    from frontx_b200 import _lib
+
+    peaks = Path(__file__).resolve().parent / "MEASURED_PEAKS.json"
+    peak, src = 6527.5, "fallback 6527.5 GB/s (copy bandwidth measured on this pool earlier)"
+    if peaks.exists():
+        try:
+            peak, src = float(json.loads(peaks.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    L = _lib.lib()
+    gen = torch.Generator(device=dev).manual_seed(3)
+    a = 0.5 + 1.5 * torch.rand((batch, 1), dtype=torch.float64, device=dev, generator=gen)
+    o = (torch.linspace(0, 20, npts, dtype=torch.float64, device=dev).unsqueeze(0) / a).contiguous()
+    theta = torch.exp(-a * o)
+    D = torch.empty_like(o)
+    status = torch.empty((batch,), dtype=torch.int32, device=dev)
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        _lib.check(L.fx_inverse_batch(batch, npts, o.data_ptr(), theta.data_ptr(), D.data_ptr(), None,
+                                      status.data_ptr(), None, None, stream.cuda_stream))
+        e1.record(stream)
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    want = (1 - torch.log(theta[:, npts // 100: npts // 2])) / (2 * a * a)
+    err = float(((D[:, npts // 100: npts // 2] - want).abs() / want).max())
+    gbs = batch * npts * 24 / best / 1e6
+    out = {"workload": f"C5: {batch} profiles x {npts} points, D at the knots", "ms": best, "bound": "hbm",
+           "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": src,
+           "status_ok": int((status == 0).sum().item()), "max_rel_dev_from_analytic_D": err}
+    del o, theta, D, want
+    torch.cuda.empty_cache()
+    return out
+
+
 def cpu_arm(models, n_sample: int, threads: int):
     """Time the oracle (CPU restatement of the reference algorithm) on the first n_sample problems."""
     from oracle import fxo
@@ -315,6 +356,14 @@ def run_ours(args) -> None:
     ok_frac = float((cnt[:, 0] == 0).mean())
     shots = {"mean": float(cnt[:, 1].mean()), "min": int(cnt[:, 1].min()), "max": int(cnt[:, 1].max())}
 
+    # ---- the other kernel of the path, for the record (not the metric): the inverse scan on config C5 ----
+    inverse_c5 = None
+    if rank == 0 and world == 1:
+        try:
+            inverse_c5 = inverse_c5_probe(dev, stream)
+        except Exception as exc:  # the metric line must not depend on it
+            inverse_c5 = {"error": str(exc)[:200]}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import fxo
@@ -350,6 +399,7 @@ def run_ours(args) -> None:
             "gpu_launches": int(launches),
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
+            "inverse_c5": inverse_c5,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
