@@ -287,7 +287,8 @@ def solve_batch(  # noqa: PLR0913
     summary = torch.empty((n, _lib.NSUM), dtype=torch.float64, device=dev)
     counters = torch.zeros((n, _lib.NCNT), dtype=torch.int32, device=dev)
     knots = torch.zeros((n, k_max, _lib.KNOT), dtype=torch.float64, device=dev) if k_max > 0 else None
-    opt = _lib.default_options(itol=float(itol), max_bisect=int(max_steps), **(options or {}))
+    opt = _lib.default_options(itol=float(itol), max_bisect=int(max_steps),
+                               **{"model_mask": models.mask(), **(options or {})})
     with torch.cuda.device(dev):
         rc = _lib.lib().fx_solve_batch(n, ids.data_ptr(), par.data_ptr(), b_t.data_ptr(), i_t.data_ptr(),
                                        opt, summary.data_ptr(), counters.data_ptr(), k_max,
@@ -398,7 +399,7 @@ def solve_flowrate_batch(  # noqa: PLR0913
     counters = torch.zeros((n, _lib.NCNT), dtype=torch.int32, device=dev)
     knots = torch.zeros((n, k_max, _lib.KNOT), dtype=torch.float64, device=dev) if k_max > 0 else None
     opt = _lib.default_options(itol=float(itol), max_bisect=int(max_steps), radial_k=radial_k, ob=float(ob),
-                               **(options or {}))
+                               **{"model_mask": models.mask(), **(options or {})})
     with torch.cuda.device(dev):
         rc = _lib.lib().fx_solve_flowrate_batch(n, ids.data_ptr(), par.data_ptr(), q_t.data_ptr(), i_t.data_ptr(),
                                                 lo_t.data_ptr(), hi_t.data_ptr(), opt, summary.data_ptr(),
@@ -452,7 +453,8 @@ def solve_batch_host(models: ModelBatch, b: np.ndarray, i: np.ndarray, *, itol: 
     if counters is None:
         counters = np.zeros((n, _lib.NCNT), dtype=np.int32)
     knots = np.zeros((n, k_max, _lib.KNOT)) if k_max > 0 else None
-    opt = _lib.default_options(itol=float(itol), max_bisect=int(max_steps), **(options or {}))
+    opt = _lib.default_options(itol=float(itol), max_bisect=int(max_steps),
+                               **{"model_mask": models.mask(), **(options or {})})
     rc = _lib.lib().fx_solve_batch_host(n, models.model_id.ctypes.data, models.params.ctypes.data,
                                         b.ctypes.data, i.ctypes.data, opt, summary.ctypes.data,
                                         counters.ctypes.data, k_max,

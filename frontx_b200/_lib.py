@@ -33,6 +33,7 @@ class SolveOptions(C.Structure):
         ("max_expansions", C.c_int32),
         ("radial_k", C.c_int32),
         ("ob", C.c_double),
+        ("model_mask", C.c_uint32),
     ]
 
 

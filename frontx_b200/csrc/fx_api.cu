@@ -7,7 +7,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
+#include <vector>
 
 #include "../../include/frontx_b200.h"
 #include "fx_inverse.cuh"
@@ -61,23 +63,27 @@ int device_info(DeviceInfo* out) {
 // scratch layout (unsigned long long): counts[8] | cursors[8] | speculation-slot allocator
 constexpr int SCR_COUNTS = 0, SCR_CURSORS = 8, SCR_WORDS = 16;
 
-__global__ void count_models_kernel(long long n, const int* __restrict__ model_id,
+// `mask` = the models the caller says are present (bit m; all seven when it does not know): a problem
+// whose model is outside it, or is no model at all, is parked in slot 7 and flagged, never solved
+__device__ __forceinline__ int bucket_of(int m, unsigned mask) {
+  return (m < 0 || m >= FX_NUM_MODELS || !((mask >> m) & 1u)) ? 7 : m;
+}
+
+__global__ void count_models_kernel(long long n, const int* __restrict__ model_id, unsigned mask,
                                     unsigned long long* scratch) {
   __shared__ unsigned int local[8];
   if (threadIdx.x < 8) local[threadIdx.x] = 0;
   __syncthreads();
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
-    int m = model_id[j];
-    if (m < 0 || m >= FX_NUM_MODELS) m = 7;  // invalid ids are parked in slot 7 and flagged
-    atomicAdd(&local[m], 1u);
+    atomicAdd(&local[bucket_of(model_id[j], mask)], 1u);
   }
   __syncthreads();
   if (threadIdx.x < 8 && local[threadIdx.x])
     atomicAdd(&scratch[SCR_COUNTS + threadIdx.x], (unsigned long long)local[threadIdx.x]);
 }
 
-__global__ void scatter_models_kernel(long long n, const int* __restrict__ model_id,
+__global__ void scatter_models_kernel(long long n, const int* __restrict__ model_id, unsigned mask,
                                       unsigned long long* scratch, int* __restrict__ perm,
                                       int* __restrict__ counters) {
   // bucket-major placement; order inside a bucket is by warp-aggregated cursor
@@ -89,11 +95,8 @@ __global__ void scatter_models_kernel(long long n, const int* __restrict__ model
   }
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
-    int m = model_id[j];
-    if (m < 0 || m >= FX_NUM_MODELS) {
-      m = 7;
-      counters[j * FX_NCNT + 0] = -1;  // invalid model id: never solved
-    }
+    const int m = bucket_of(model_id[j], mask);
+    if (m == 7) counters[j * FX_NCNT + 0] = FX_INVALID_MODEL;  // never solved
     unsigned long long pos = atomicAdd(&scratch[SCR_CURSORS + m], 1ull);
     perm[base[m] + (long long)pos] = (int)j;
   }
@@ -164,37 +167,60 @@ int launch_by_id(int model, const fx::SolveArgs& a, int geom, long long n_upper,
   }
 }
 
-// per-device helper streams/events used to run the per-model launches side by side
+// Helper streams and events that run the per-model launches of one call side by side.  One set per
+// (device, caller stream): two host threads solving on two streams share nothing, and a set's mutex is
+// held for the whole fork/join enqueue section of a call so that record/wait pairs never interleave.
 struct Fork {
+  int dev = -1;
+  cudaStream_t owner = nullptr;
   cudaStream_t streams[FX_NUM_MODELS] = {};
   cudaEvent_t begin = nullptr, done[FX_NUM_MODELS] = {};
   cudaEvent_t k0[FX_NUM_MODELS] = {}, k1[FX_NUM_MODELS] = {};  // kernel timing (fx_set_kernel_timing)
   bool timed[FX_NUM_MODELS] = {};
-  bool ok = false;
+  std::mutex mu;
 };
 
 std::atomic<int> g_kernel_timing{0};
+std::mutex g_fork_mu;
+std::vector<std::unique_ptr<Fork>> g_forks;
+Fork* g_last_timed[64][FX_NUM_MODELS] = {};  // per device: the set that holds the latest timed launch of a model
+constexpr size_t MAX_FORKS = 64;             // beyond that many (device, stream) pairs, sets are shared
 
-int get_fork(Fork** out) {
+int get_fork(cudaStream_t owner, Fork** out) {
   int dev = 0;
   FX_CUDA(cudaGetDevice(&dev));
-  static std::mutex mu;
-  static Fork forks[64];
-  std::lock_guard<std::mutex> lk(mu);
-  Fork& f = forks[dev];
-  if (!f.ok) {
-    for (int m = 0; m < FX_NUM_MODELS; m++) {
-      FX_CUDA(cudaStreamCreateWithFlags(&f.streams[m], cudaStreamNonBlocking));
-      FX_CUDA(cudaEventCreateWithFlags(&f.done[m], cudaEventDisableTiming));
-      FX_CUDA(cudaEventCreate(&f.k0[m]));
-      FX_CUDA(cudaEventCreate(&f.k1[m]));
-    }
-    FX_CUDA(cudaEventCreateWithFlags(&f.begin, cudaEventDisableTiming));
-    f.ok = true;
+  std::lock_guard<std::mutex> lk(g_fork_mu);
+  Fork* same_dev = nullptr;
+  for (auto& f : g_forks) {
+    if (f->dev != dev) continue;
+    if (f->owner == owner) { *out = f.get(); return FX_OK; }
+    same_dev = f.get();
   }
-  *out = &f;
+  if (g_forks.size() >= MAX_FORKS && same_dev) { *out = same_dev; return FX_OK; }
+  std::unique_ptr<Fork> f(new Fork);
+  f->dev = dev;
+  f->owner = owner;
+  for (int m = 0; m < FX_NUM_MODELS; m++) {
+    FX_CUDA(cudaStreamCreateWithFlags(&f->streams[m], cudaStreamNonBlocking));
+    FX_CUDA(cudaEventCreateWithFlags(&f->done[m], cudaEventDisableTiming));
+    FX_CUDA(cudaEventCreate(&f->k0[m]));
+    FX_CUDA(cudaEventCreate(&f->k1[m]));
+  }
+  FX_CUDA(cudaEventCreateWithFlags(&f->begin, cudaEventDisableTiming));
+  *out = f.get();
+  g_forks.push_back(std::move(f));
   return FX_OK;
 }
+
+// stream-ordered scratch of one call, released on every way out of it
+struct Scratch {
+  cudaStream_t s;
+  void* p = nullptr;
+  explicit Scratch(cudaStream_t s_) : s(s_) {}
+  ~Scratch() { if (p) cudaFreeAsync(p, s); }
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+};
 
 int check_options(const fx_solve_options* in, fx_solve_options* o) {
   if (in) *o = *in; else fx_default_solve_options(o);
@@ -203,6 +229,7 @@ int check_options(const fx_solve_options* in, fx_solve_options* o) {
     return fail(FX_ERR_ARG, "invalid solve options%s");
   if (o->radial_k < 0 || o->radial_k > 2) return fail(FX_ERR_ARG, "radial_k must be 0, 1 or 2%s");
   if (o->radial_k > 0 && !(o->ob > 0.0)) return fail(FX_ERR_ARG, "radial problems need ob > 0%s");
+  if (o->model_mask >> FX_NUM_MODELS) return fail(FX_ERR_ARG, "model_mask has bits beyond the known models%s");
   return FX_OK;
 }
 
@@ -485,6 +512,7 @@ void fx_default_solve_options(fx_solve_options* o) {
   o->max_expansions = 64;
   o->radial_k = 0;
   o->ob = 0.0;
+  o->model_mask = 0;
 }
 
 const char* fx_last_error(void) { return g_err; }
@@ -496,9 +524,15 @@ void fx_set_kernel_timing(int on) { g_kernel_timing.store(on ? 1 : 0); }
 
 int fx_last_solve_kernel_ms(int model, float* ms) {
   if (model < 0 || model >= FX_NUM_MODELS || !ms) return fail(FX_ERR_ARG, "bad model id or null pointer%s");
+  int dev = 0;
+  FX_CUDA(cudaGetDevice(&dev));
   Fork* fk = nullptr;
-  int rc = get_fork(&fk);
-  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(g_fork_mu);
+    if (dev >= 0 && dev < 64) fk = g_last_timed[dev][model];
+  }
+  if (!fk) return fail(FX_ERR_ARG, "no timed launch recorded: call fx_set_kernel_timing(1) first%s");
+  std::lock_guard<std::mutex> lk(fk->mu);
   if (!fk->timed[model]) return fail(FX_ERR_ARG, "no timed launch recorded: call fx_set_kernel_timing(1) first%s");
   FX_CUDA(cudaEventSynchronize(fk->k1[model]));
   FX_CUDA(cudaEventElapsedTime(ms, fk->k0[model], fk->k1[model]));
@@ -550,39 +584,47 @@ int solve_impl(int64_t n, const int32_t* model_id, const double* params, const d
   if (rc) return rc;
   DeviceInfo di;
   if ((rc = device_info(&di))) return rc;
-  Fork* fk = nullptr;
-  if ((rc = get_fork(&fk))) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  Fork* fk = nullptr;
+  if ((rc = get_fork(s, &fk))) return rc;
 
-  // scratch, stream-ordered: bucket counters + permutation, the queue control blocks, the shot
-  // ring (one region per bucket: its problems + one spare entry per resident lane), 8 bytes of
-  // bisection state per problem, and the speculation slots
+  // The caller may say which models the batch holds (opt->model_mask): only those get a ring region and a
+  // launch.  Without the hint every model is launched and the empty buckets' grids exit at once.
+  const unsigned mask = o.model_mask ? o.model_mask : ((1u << FX_NUM_MODELS) - 1u);
+  int n_regions = 0, region_of[FX_NUM_MODELS];
+  for (int m = 0; m < FX_NUM_MODELS; m++) region_of[m] = ((mask >> m) & 1u) ? n_regions++ : 0;
+
+  // Scratch, ONE stream-ordered allocation: bucket counters and cursors, the speculation-slot allocator,
+  // the queue control blocks, 8 bytes of bisection state per problem, the shot ring (one region per
+  // bucket present: its problems + one spare entry per resident lane) -- all of that zeroed by one
+  // memset -- then the bucket-major permutation and the speculation slots.
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
   const long long max_lanes = (long long)di.sms * 2048;
   const long long ring_pad = max_lanes + 64;
-  const size_t ring_words = (size_t)n + 8 * (size_t)ring_pad;
-  long long spec_slots = (long long)di.sms * 512 + 8;  // >= resident lanes at 128 registers/thread
+  const size_t ring_words = (size_t)n + (size_t)n_regions * (size_t)ring_pad;
+  // one slot per problem that ever speculates (it keeps it): ~116 MB of pool memory whatever the depth
+  long long spec_slots = (long long)di.sms * (16384 / fx::SPEC_NODES) + 8;
   if (spec_slots > n) spec_slots = n;
-  if (k_max > 0) spec_slots = 0;  // dense output requested: the last shot must write its knots itself
-  unsigned long long* scratch = nullptr;
-  int* perm = nullptr;
-  fx::QueueCtl* ctl = nullptr;
-  unsigned long long* ring = nullptr;
-  int2* bstate = nullptr;
-  fx::SpecEntry* spec = nullptr;
-  FX_CUDA(cudaMallocAsync((void**)&scratch, (SCR_WORDS + 8) * sizeof(unsigned long long), s));
-  FX_CUDA(cudaMallocAsync((void**)&perm, (size_t)n * sizeof(int), s));
-  FX_CUDA(cudaMallocAsync((void**)&ctl, 8 * sizeof(fx::QueueCtl), s));
-  FX_CUDA(cudaMallocAsync((void**)&ring, ring_words * sizeof(unsigned long long), s));
-  FX_CUDA(cudaMallocAsync((void**)&bstate, (size_t)n * sizeof(int2), s));
-  if (spec_slots > 0)
-    FX_CUDA(cudaMallocAsync((void**)&spec, (size_t)spec_slots * fx::SPEC_NODES * sizeof(fx::SpecEntry), s));
-  FX_CUDA(cudaMemsetAsync(scratch, 0, (SCR_WORDS + 8) * sizeof(unsigned long long), s));
-  FX_CUDA(cudaMemsetAsync(ring, 0, ring_words * sizeof(unsigned long long), s));
-  FX_CUDA(cudaMemsetAsync(bstate, 0, (size_t)n * sizeof(int2), s));
+  const size_t off_ctl = up((SCR_WORDS + 8) * sizeof(unsigned long long));
+  const size_t off_bstate = off_ctl + up(8 * sizeof(fx::QueueCtl));
+  const size_t off_ring = off_bstate + up((size_t)n * sizeof(int2));
+  const size_t off_perm = off_ring + up(ring_words * sizeof(unsigned long long));
+  const size_t off_spec = off_perm + up((size_t)n * sizeof(int));
+  const size_t total = off_spec + (size_t)spec_slots * fx::SPEC_NODES * sizeof(fx::SpecEntry);
+  Scratch scr(s);
+  FX_CUDA(cudaMallocAsync(&scr.p, total, s));
+  char* base = static_cast<char*>(scr.p);
+  unsigned long long* scratch = reinterpret_cast<unsigned long long*>(base);
+  fx::QueueCtl* ctl = reinterpret_cast<fx::QueueCtl*>(base + off_ctl);
+  int2* bstate = reinterpret_cast<int2*>(base + off_bstate);
+  unsigned long long* ring = reinterpret_cast<unsigned long long*>(base + off_ring);
+  int* perm = reinterpret_cast<int*>(base + off_perm);
+  fx::SpecEntry* spec = spec_slots > 0 ? reinterpret_cast<fx::SpecEntry*>(base + off_spec) : nullptr;
+  FX_CUDA(cudaMemsetAsync(base, 0, off_perm, s));
   int g = grid_for(n, 256, di.sms);
-  count_models_kernel<<<g, 256, 0, s>>>(n, model_id, scratch);
+  count_models_kernel<<<g, 256, 0, s>>>(n, model_id, mask, scratch);
   g_launches++;
-  scatter_models_kernel<<<g, 256, 0, s>>>(n, model_id, scratch, perm, counters);
+  scatter_models_kernel<<<g, 256, 0, s>>>(n, model_id, mask, scratch, perm, counters);
   g_launches++;
   fx::init_queues_kernel<<<1, 32, 0, s>>>(scratch + SCR_COUNTS, ctl);
   g_launches++;
@@ -616,19 +658,33 @@ int solve_impl(int64_t n, const int32_t* model_id, const double* params, const d
   a.max_ode_steps = o.max_ode_steps;
   a.max_expansions = o.max_expansions;
   a.radial_k = o.radial_k;
+  a.sms = di.sms;
 
-  // fork: one persistent launch per model, side by side; empty buckets exit at once
-  FX_CUDA(cudaEventRecord(fk->begin, s));
-  for (int m = 0; m < FX_NUM_MODELS; m++) {
-    FX_CUDA(cudaStreamWaitEvent(fk->streams[m], fk->begin, 0));
-    a.slot = m;
+  {
+    // fork: one persistent launch per model present, side by side; the set is this call's until the join
+    std::lock_guard<std::mutex> lk(fk->mu);
     const bool timing = g_kernel_timing.load() != 0;
-    if (timing) FX_CUDA(cudaEventRecord(fk->k0[m], fk->streams[m]));
-    if ((rc = launch_by_id(m, a, q ? 2 : (o.radial_k > 0 ? 1 : 0), n, di.sms, fk->streams[m]))) return rc;
-    if (timing) FX_CUDA(cudaEventRecord(fk->k1[m], fk->streams[m]));
-    fk->timed[m] = timing;
-    FX_CUDA(cudaEventRecord(fk->done[m], fk->streams[m]));
-    FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
+    const int geom = q ? 2 : (o.radial_k > 0 ? 1 : 0);
+    FX_CUDA(cudaEventRecord(fk->begin, s));
+    for (int m = 0; m < FX_NUM_MODELS; m++) {
+      if (!((mask >> m) & 1u)) continue;
+      FX_CUDA(cudaStreamWaitEvent(fk->streams[m], fk->begin, 0));
+      a.slot = m;
+      a.ring_region = region_of[m];
+      if (timing) FX_CUDA(cudaEventRecord(fk->k0[m], fk->streams[m]));
+      if ((rc = launch_by_id(m, a, geom, n, di.sms, fk->streams[m]))) return rc;
+      if (timing) FX_CUDA(cudaEventRecord(fk->k1[m], fk->streams[m]));
+      fk->timed[m] = timing;
+      FX_CUDA(cudaEventRecord(fk->done[m], fk->streams[m]));
+      FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
+    }
+    if (timing) {
+      std::lock_guard<std::mutex> lk2(g_fork_mu);
+      int dev = fk->dev;
+      if (dev >= 0 && dev < 64)
+        for (int m = 0; m < FX_NUM_MODELS; m++)
+          if ((mask >> m) & 1u) g_last_timed[dev][m] = fk;
+    }
   }
   if (q) {
     // flow-rate boundary: d_dob = -q/D(b) and D(b) at the accepted b, by the same evaluation the shots used
@@ -636,13 +692,7 @@ int solve_impl(int64_t n, const int32_t* model_id, const double* params, const d
     g_launches++;
     FX_CUDA(cudaGetLastError());
   }
-  if (spec) FX_CUDA(cudaFreeAsync(spec, s));
-  FX_CUDA(cudaFreeAsync(bstate, s));
-  FX_CUDA(cudaFreeAsync(ring, s));
-  FX_CUDA(cudaFreeAsync(ctl, s));
-  FX_CUDA(cudaFreeAsync(perm, s));
-  FX_CUDA(cudaFreeAsync(scratch, s));
-  return FX_OK;
+  return FX_OK;  // ~Scratch returns the scratch to the pool in stream order
 }
 
 }  // namespace
@@ -657,8 +707,13 @@ int fx_solve_batch_host(int64_t n, const int32_t* model_id, const double* params
   if (!model_id || !params || !b || !i || !summary || !counters)
     return fail(FX_ERR_ARG, "null pointer argument%s");
   if (k_max > 0 && !knots) return fail(FX_ERR_ARG, "k_max > 0 needs a knots buffer%s");
-  cudaStream_t s = nullptr;
-  FX_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  // one stream per host thread and device, kept: its fork set (get_fork) is then reused call after call
+  thread_local cudaStream_t t_stream[64] = {};
+  int dev = 0;
+  FX_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return fail(FX_ERR_CUDA, "device index out of range%s");
+  if (!t_stream[dev]) FX_CUDA(cudaStreamCreateWithFlags(&t_stream[dev], cudaStreamNonBlocking));
+  cudaStream_t s = t_stream[dev];
   int32_t *d_model = nullptr, *d_cnt = nullptr;
   double *d_par = nullptr, *d_b = nullptr, *d_i = nullptr, *d_sum = nullptr, *d_knots = nullptr;
   size_t nn = (size_t)n;
@@ -690,7 +745,6 @@ int fx_solve_batch_host(int64_t n, const int32_t* model_id, const double* params
   for (void* p : bufs)
     if (p) cudaFreeAsync(p, s);
   cudaStreamSynchronize(s);
-  cudaStreamDestroy(s);
   return rc;
 }
 

@@ -64,6 +64,7 @@ FX_HD void derive_params(const double* p, double (&d)[NDERIVED], const MathTab& 
     d[5] = dT;
     d[6] = 1.0 / dT;
     d[7] = 1.0 / d[3];
+    d[8] = p[7];  // form of 1 - Se^(1/m): 0 the reference's literal subtraction, else cancellation-free
   } else if constexpr (MODEL == FX_LETD) {
     double tr = p[4], ts = p[5];
     double dT = ts - tr;
@@ -137,9 +138,11 @@ FX_HD void eval_D(const double (&d)[NDERIVED], double theta, bool want2, double&
     double im = d[0], m = d[1], a = d[2], Cc = d[3], tr = d[4], dT = d[5], idT = d[6], iCc = d[7];
     double Se = div_by(theta - tr, dT, idT);
     double L = fx_log(Se, T);
-    // w = 1 - Se^(1/m) has condition number ~1e7 at b = theta_s - 1e-7 (the reference's own
-    // test point); form it without cancellation so that implementations agree to ~1e-15
-    double w = -fx_expm1(im * L, T);
+    // w = 1 - Se^(1/m) has condition number ~1e7 at b = theta_s - 1e-7 (the reference's own test
+    // point).  By default it is the LITERAL subtraction 1 - fx_exp(log(Se)/m), as models.py:245,253
+    // write it (the rounding of Se^(1/m) is then ~1e-9 of w there, and differs between pow()
+    // implementations); params[7] != 0 asks for the cancellation-free -expm1(log(Se)/m) instead.
+    double w = -fx_expm1(im * L, T, d[8] != 0.0);
     double u = 1.0 - w;                     // Se^(1/m)
     double v = fx_exp(m * fx_log(w, T), T); // (1 - Se^(1/m))^m
     double omv = 1.0 - v;

@@ -56,10 +56,31 @@
 
 namespace fx {
 
-constexpr int SOLVE_BLOCK = 128;
-constexpr int SOLVE_CTAS_PER_SM = 5;             // <= 96 registers per thread: 5 warps per SM sub-partition
-constexpr int SPEC_MAX_DEPTH = 5;                // up to 31 speculative shots per problem
+// Scheduling knobs (results never depend on them; scripts/exp_variants.py builds and times variants):
+#ifndef FX_SOLVE_BLOCK
+#define FX_SOLVE_BLOCK 128
+#endif
+#ifndef FX_SOLVE_CTAS
+#define FX_SOLVE_CTAS 5      // <= 96 registers per thread: 5 warps per SM sub-partition
+#endif
+#ifndef FX_SPEC_MAX_DEPTH
+#define FX_SPEC_MAX_DEPTH 5  // up to 2^depth - 1 speculative shots per problem and round
+#endif
+#ifndef FX_LATE_NBIS
+#define FX_LATE_NBIS 0       // > 0: a bisection that has taken this many steps without converging is
+#endif                       // probably one of the ~0.5 % that never will: speculate at once, FX_LATE_DEPTH
+#ifndef FX_LATE_DEPTH        // levels per round, while the bulk of the batch still fills the lanes
+#define FX_LATE_DEPTH 4
+#endif
+#ifndef FX_TAIL_DENSE
+#define FX_TAIL_DENSE 0      // 1: in the end phase only as many CTA layers as the outstanding shots can fill
+#endif                       // take work (full warps, few warps per scheduler), the rest drain and sleep
+constexpr int SOLVE_BLOCK = FX_SOLVE_BLOCK;
+constexpr int SOLVE_CTAS_PER_SM = FX_SOLVE_CTAS;
+constexpr int SPEC_MAX_DEPTH = FX_SPEC_MAX_DEPTH;
+static_assert(SPEC_MAX_DEPTH >= 1 && SPEC_MAX_DEPTH <= 7, "a ring entry carries the tree node in 8 bits");
 constexpr int SPEC_NODES = 1 << SPEC_MAX_DEPTH;  // entries per speculation slot (entry 0 = header)
+constexpr int REPLAY_NODE = 255;                 // ring code of "integrate the accepted shot again, for its knots"
 constexpr int FX_IN_FLIGHT = -3;                 // counters[.][0] while a problem is unfinished: if a launch ever
                                                  // ended early (ctl->abort), such problems do not read as solved
 
@@ -91,6 +112,7 @@ struct SpecEntry {
 struct SolveArgs {
   const unsigned long long* counts;  // per-model bucket sizes (device)
   int slot;                  // this launch's bucket
+  int ring_region;           // which of the ring's per-bucket regions it owns (buckets absent from the batch have none)
   const int* perm;           // bucket-major list of problem indices
   const double* params;      // [N][12]
   const double* b;           // [N]  boundary value; with a flow-rate boundary: lower end of the bracket on b
@@ -110,6 +132,7 @@ struct SolveArgs {
   unsigned int spec_slots;
   double itol, rtol, atol, ob;
   int max_bisect, max_ode_steps, max_expansions, radial_k;
+  int sms;                   // SMs of the device: CTA b is taken to be the (b / sms)-th resident CTA of its SM
 };
 
 enum Mode : int { M_FETCH = 0, M_DB = 1, M_INIT0 = 2, M_INIT1 = 3, M_CHORD = 4, M_DONE = 5, M_WAIT = 6 };
@@ -160,7 +183,7 @@ __device__ __forceinline__ double node_midpoint(double lower, double upper, int 
 template <int MODEL>
 struct DerivedCount {
   static constexpr int value = MODEL == FX_CONSTANT ? 2 : MODEL == FX_POWER_LAW ? 4 : MODEL == FX_LOG ? 2 :
-                               MODEL == FX_BROOKS_COREY ? 6 : MODEL == FX_VAN_GENUCHTEN ? 8 :
+                               MODEL == FX_BROOKS_COREY ? 6 : MODEL == FX_VAN_GENUCHTEN ? 9 :
                                MODEL == FX_LETD ? 8 : 11;
 };
 
@@ -220,13 +243,15 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     if ((long long)blockIdx.x >= share) ctx.n_work = 0;  // this CTA is not needed
     ctx.perm = A.perm + off;
     ctx.ctl = A.ctl + A.slot;
-    ctx.ring = A.ring + off + (long long)A.slot * A.ring_pad;
+    ctx.ring = A.ring + off + (long long)A.ring_region * A.ring_pad;
     ctx.ring_cap = ctx.n_work + A.ring_pad;
     ctx.n_lanes = share * SOLVE_BLOCK;
   }
   __syncthreads();
   if (ctx.n_work == 0) return;
-  const bool can_speculate = (A.knots == nullptr) && (A.spec_slots > 0);
+  // Speculative shots do not write knots; when the bisection ends on one, the accepted shot is
+  // integrated once more (node = -1) to write the dense output -- one shot more than the ~18 of a solve.
+  const bool can_speculate = A.spec_slots > 0;
 
   // ---- per-lane state (registers) ---------------------------------------
   int mode = M_FETCH;
@@ -270,9 +295,23 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
         const long long rem = *(volatile long long*)&ctl->remaining;
         const unsigned int ab = *(volatile unsigned int*)&ctl->abort;
         sparse_now = rem * 16 < ctx.n_lanes;
+        bool allowed = true;
+#if FX_TAIL_DENSE
+        if (sparse_now && A.sms > 0 && gridDim.x >= (unsigned)A.sms) {
+          // End phase: the unfinished problems' batches need rem * (2^depth - 1) lanes.  Only the first
+          // `layers` resident CTAs of every SM take work -- full warps on few warp slots per scheduler,
+          // where a trip costs its latency instead of its share of the issue slots -- the rest drain.
+          const long long per_layer = (long long)A.sms * SOLVE_BLOCK;
+          const long long want = rem * ((1LL << SPEC_MAX_DEPTH) - 1);
+          const long long layers = (want + per_layer - 1) / per_layer;
+          allowed = (long long)(blockIdx.x / (unsigned)A.sms) < (layers < 1 ? 1 : layers);
+          sparse_now = false;  // the working CTAs pack their warps
+          if (!allowed) sparse_now = true;
+        }
+#endif
         if (rem <= 0 || ab) {
           got = -1;
-        } else if (*(volatile long long*)&ctl->avail > 0) {
+        } else if (allowed && *(volatile long long*)&ctl->avail > 0) {
           long long old = (long long)atomicAdd((unsigned long long*)&ctl->avail,
                                                (unsigned long long)(-(long long)want));
           got = old >= want ? want : (old > 0 ? old : 0);
@@ -314,6 +353,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
             __threadfence();
             prob = (int)(unsigned int)(e & 0xffffffffull);
             node = (int)((e >> 32) & 0xff);
+            if (node == REPLAY_NODE) node = -1;
           }
           if (lost) {
             mode = M_DONE;
@@ -348,7 +388,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
                 const double* S = A.summary + (size_t)prob * FX_NSUM;
                 const double lower = __ldcg(S + 6), upper = __ldcg(S + 7);
                 const int phase = __ldcg(&A.bstate[prob].x) & 3;
-                d_shot = (phase == 0) ? lower : (phase == 1) ? upper : node_midpoint(lower, upper, node ? node : 1);
+                d_shot = (node < 0) ? __ldcg(S + 0)
+                         : (phase == 0) ? lower : (phase == 1) ? upper : node_midpoint(lower, upper, node ? node : 1);
               }
               s_cold[FLOW ? 5 : 0][tid] = A.q[prob];
               mode = M_DB;  // D(b) of this shot's b: d_dob = -q/D(b)
@@ -359,7 +400,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
               const double* S = A.summary + (size_t)prob * FX_NSUM;
               const double lower = __ldcg(S + 6), upper = __ldcg(S + 7);
               const int phase = __ldcg(&A.bstate[prob].x) & 3;
-              d_shot = (phase == 0) ? lower : (phase == 1) ? upper : node_midpoint(lower, upper, node ? node : 1);
+              d_shot = (node < 0) ? __ldcg(S + 0)
+                       : (phase == 0) ? lower : (phase == 1) ? upper : node_midpoint(lower, upper, node ? node : 1);
               t0 = A.ob;
               y00 = bnd_b;
               y01 = d_shot;
@@ -374,7 +416,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       }
       if (!busy) {
         if (got == 0) {
-          __nanosleep(sparse ? 500u : idle_ns);
+          __nanosleep(sparse ? (FX_TAIL_DENSE ? 4000u : 500u) : idle_ns);
           if (idle_ns < 16000u) idle_ns *= 2;
         } else {
           idle_ns = 1000u;
@@ -436,7 +478,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       rhs_shot++;
       fsm[0][tid][0] = R.F0;
       fsm[0][tid][1] = R.F1;
-      if (A.knots && node == 0 && A.k_max > 0)
+      if (A.knots && node <= 0 && A.k_max > 0)
         *reinterpret_cast<double4*>(A.knots + (size_t)prob * A.k_max * FX_KNOT) = make_double4(t0, y00, y01, R.F1);
       n_knots = 1;
       double h0, d1;
@@ -507,7 +549,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
         y01 = s.y11;
         fsm[0][tid][0] = f0;  // FSAL
         fsm[0][tid][1] = f1;
-        if (A.knots && node == 0 && n_knots < A.k_max) {
+        if (A.knots && node <= 0 && n_knots < A.k_max) {
           double* knot_row = A.knots + (size_t)prob * A.k_max * FX_KNOT;
           *reinterpret_cast<double4*>(knot_row + (size_t)n_knots * FX_KNOT) = make_double4(t0, y00, y01, f1);
         }
@@ -532,7 +574,12 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     }
 
     // ---- end of a shot: fold it into the problem's bisection ----------------
-    if (shot_end) {
+    if (shot_end && node < 0) {
+      // the accepted shot, integrated again for its dense output: the problem is done
+      __threadfence();
+      atomicAdd((unsigned long long*)&ctx.ctl->remaining, (unsigned long long)(-1LL));
+      mode = M_FETCH;
+    } else if (shot_end) {
       const double res = occurred ? (y00 - bnd_i) : direction * fx_inf();  // _forward.py:97-101
       double* S = A.summary + (size_t)prob * FX_NSUM;
       int4* C = reinterpret_cast<int4*>(A.counters + (size_t)prob * FX_NCNT);
@@ -616,7 +663,13 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
           __stcg(s2 + 3, make_double2(bis.lower, bis.upper));
           __stcg(C, make_int4(result, n_shots, bis.n_exp, n_att));
           __stcg(C + 1, make_int4(n_rej, n_rhs, n_att, e.knots));
-          atomicAdd((unsigned long long*)&ctx.ctl->remaining, (unsigned long long)(-1LL));
+          if (A.knots && node > 0) {
+            // the knots in memory are those of an earlier ordinary shot: run the accepted one again
+            __threadfence();
+            push_tasks(ctx.ctl, ctx.ring, ctx.n_work, ctx.ring_cap, prob, REPLAY_NODE, 1);
+          } else {
+            atomicAdd((unsigned long long*)&ctx.ctl->remaining, (unsigned long long)(-1LL));
+          }
         } else {
           // not converged: save the bisection state and queue the problem's next shot(s)
           __stcg(S + 6, bis.lower);
@@ -638,6 +691,10 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
               const unsigned u = (((unsigned)prob * 2654435761u) ^ ((unsigned)n_shots * 40503u)) >> 24;
               if ((rho - lo) * 256 > (hi - lo) * (long long)u) d++;
             }
+#if FX_LATE_NBIS > 0
+            if (bis.n_bis >= FX_LATE_NBIS && d < (FX_LATE_DEPTH < SPEC_MAX_DEPTH ? FX_LATE_DEPTH : SPEC_MAX_DEPTH))
+              d = FX_LATE_DEPTH < SPEC_MAX_DEPTH ? FX_LATE_DEPTH : SPEC_MAX_DEPTH;
+#endif
             if (d > 1 && bs.y == 0) {
               unsigned int sl = atomicAdd(A.spec_next, 1u);
               if (sl < A.spec_slots) bs.y = (int)sl + 1; else d = 1;

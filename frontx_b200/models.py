@@ -60,6 +60,8 @@ class _TaggedModel:
                 conv[key] = None
             elif key == "theta_range":
                 conv[key] = (np.asarray(v[0], dtype=np.float64), np.asarray(v[1], dtype=np.float64))
+            elif isinstance(v, str):
+                conv[key] = v
             else:
                 conv[key] = np.asarray(v, dtype=np.float64)
         cols = np.broadcast_arrays(*[np.asarray(c, dtype=np.float64) for c in cls(**conv)._pack()])
@@ -159,7 +161,13 @@ class BrooksAndCorey(_TaggedModel):
 class VanGenuchten(_TaggedModel):
     """van Genuchten-Mualem, ``D = K/C`` (src/frontx/models.py:177-253).
 
-    Either ``n`` or ``m`` must be given; the other follows from ``m = 1 - 1/n``.
+    Either ``n`` or ``m`` must be given; the other follows from ``m = 1 - 1/n``.  The kernels use the
+    Mualem constraint ``m = 1 - 1/n`` in closed form, so a pair that violates it is refused (the
+    reference would evaluate the unconstrained expression).
+
+    ``form`` selects how ``1 - Se**(1/m)`` is formed: ``"literal"`` (default) is the subtraction the
+    reference writes (src/frontx/models.py:245,253), which cancels ~7 digits at ``b = theta_s - 1e-7``;
+    ``"expm1"`` is the same value without the cancellation.
     """
 
     n: float | None = None
@@ -172,6 +180,7 @@ class VanGenuchten(_TaggedModel):
     mu: float = 1e-3
     alpha: float = 1
     theta_range: tuple = (0, 1)
+    form: str = "literal"
     model_id = _lib.VAN_GENUCHTEN
 
     @property
@@ -194,7 +203,15 @@ class VanGenuchten(_TaggedModel):
 
     def _pack(self):
         Ks = _resolve_Ks(self.Ks, self.k, self.g, self.rho, self.mu)
-        return [self._n, self._m, self.l, Ks, self.alpha, self.theta_range[0], self.theta_range[1]]
+        if self.form not in ("literal", "expm1"):
+            msg = "form must be 'literal' or 'expm1'"
+            raise ValueError(msg)
+        n, m = self._n, self._m
+        if self.n is not None and self.m is not None and np.any(np.abs(np.asarray(m) - (1 - 1 / np.asarray(n))) > 1e-12):
+            msg = "the kernels need m = 1 - 1/n; give n or m, not an inconsistent pair"
+            raise ValueError(msg)
+        return [n, m, self.l, Ks, self.alpha, self.theta_range[0], self.theta_range[1],
+                0.0 if self.form == "literal" else 1.0]
 
 
 @dataclass(frozen=True)
@@ -253,6 +270,12 @@ class ModelBatch:
     def __getitem__(self, idx) -> "ModelBatch":
         ids = np.atleast_1d(self.model_id[idx])
         return ModelBatch(ids, self.params[idx].reshape(ids.size, _lib.NPARAM))
+
+    def mask(self) -> int:
+        """Bit m set = model id m occurs in the batch (``fx_solve_options.model_mask``: only those models are
+        launched; ids the library does not know contribute nothing and are flagged by the kernels)."""
+        ids = np.unique(self.model_id)
+        return int(sum(1 << int(m) for m in ids if 0 <= m < len(_lib.MODEL_NAMES)))
 
     def saturation(self, margin: float = 1e-7) -> np.ndarray:
         """Largest boundary value worth bracketing per problem: ``theta_s - margin*(theta_s - theta_r)``

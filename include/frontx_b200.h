@@ -47,7 +47,9 @@ extern "C" {
  *   FX_POWER_LAW      {a, k, eps}                            D = a*theta^k+eps (fronts.D.power_law;
  *                                                            tests/test_solve.py:151 D=theta)
  *   FX_BROOKS_COREY   {n, l, Ks, alpha, theta_r, theta_s}    src/frontx/models.py:126-174
- *   FX_VAN_GENUCHTEN  {n, m, l, Ks, alpha, theta_r, theta_s} src/frontx/models.py:177-253
+ *   FX_VAN_GENUCHTEN  {n, m, l, Ks, alpha, theta_r, theta_s, form}  src/frontx/models.py:177-253
+ *                     (m = 1 - 1/n; form = 0: 1 - Se^(1/m) by the literal subtraction of :245,253,
+ *                      form = 1: the same value without cancellation, -expm1(log(Se)/m))
  *   FX_LETXS          {Lw, Ew, Tw, Ls, Es, Ts, Ks, alpha, theta_r, theta_s}  models.py:256-315
  *   FX_LETD           {L, E, T, Dwt, theta_r, theta_s}       src/frontx/models.py:35-66
  *   FX_LOG            {c0, c1}      D = c0 + c1*ln(theta)    tests/test_solve.py:40 (Philip 1960)
@@ -94,6 +96,9 @@ typedef struct fx_solve_options {
   int32_t max_expansions; /* 64    bound on Bisection(expand_if_necessary=True) */
   int32_t radial_k;      /* 0 planar (the reference); 1 cylindrical/polar, 2 spherical */
   double ob;             /* 0 for the reference; >0 only with radial_k>0 */
+  uint32_t model_mask;   /* optional hint: bit m set = problems of enum fx_model m may occur.  0 = unknown
+                            (every model is launched; empty ones exit at once).  A problem whose model is
+                            outside a non-zero mask is not solved and reports FX_INVALID_MODEL.           */
 } fx_solve_options;
 
 void fx_default_solve_options(fx_solve_options *opt);
@@ -101,8 +106,10 @@ void fx_default_solve_options(fx_solve_options *opt);
 /* Replaces frontx.solve (src/frontx/_forward.py:60-122) for a batch of n
  * independent problems: Kvaerno5 ESDIRK shots (diffrax, :84-95) with the boolean
  * event (:76-78), bisection on d_dob (:104-112).  Persistent lanes pop single
- * shots from a device-wide queue (fx_solve.cuh); with k_max = 0 idle lanes also run
- * the next levels of a problem's bisection tree speculatively (same results).
+ * shots from a device-wide queue (fx_solve.cuh); idle lanes also run the next levels of a
+ * problem's bisection tree speculatively (same results; with dense output the accepted shot is
+ * then integrated once more to write its knots).  Safe to call from several host threads on
+ * distinct streams.
  * k_max = 0 skips dense output; otherwise knots is [n][k_max][4] and
  * rows hold the last shot's accepted steps (n_knots may exceed k_max: the table
  * is then truncated and Solution evaluation refuses it).  All pointers device. */

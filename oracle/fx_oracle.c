@@ -81,8 +81,11 @@ static jet Se_of(double theta, double theta_r, double theta_s) {
   return r;
 }
 
-static int g_vg_literal = 0;
-void fxo_set_vg_literal(int on) { g_vg_literal = on; }
+/* diagnostics summed over every solve since the last reset (tests: which of the uncertain
+ * dependency semantics, SURVEY.md Appendix A U4-U6, a workload actually exercises) */
+static atomic_llong g_diag[FXO_NDIAG];
+void fxo_diag_reset(void) { for (int k = 0; k < FXO_NDIAG; k++) atomic_store(&g_diag[k], 0); }
+void fxo_diag_get(int64_t *out) { for (int k = 0; k < FXO_NDIAG; k++) out[k] = (int64_t)atomic_load(&g_diag[k]); }
 
 /* D(theta) as a jet, from the reference definitions */
 static jet D_jet(int model, const double *p, double theta) {
@@ -114,15 +117,16 @@ static jet D_jet(int model, const double *p, double theta) {
       double n = p[0], m = p[1], l = p[2], Ks = p[3], alpha = p[4];
       jet Se = Se_of(theta, p[5], p[6]);
       jet u = j_powc(Se, 1.0 / m);
-      /* 1 - Se^(1/m) has condition number ~1e7 at the reference's own test point
-       * b = theta_s - 1e-7: the literal subtraction carries ~1e-9 relative rounding noise that
-       * differs between pow() implementations (glibc, XLA, CUDA) and that the shooting
-       * problem amplifies ~1e4-fold.  By default the VALUE of (1 - u) is formed without
-       * cancellation, -expm1(log(Se)/m); every other term is the literal expression.
-       * fxo_set_vg_literal(1) restores the literal subtraction (tests measure the gap). */
+      /* models.py:245,253 form 1 - Se**(1/m) by the literal subtraction, which at the reference's own
+       * test point b = theta_s - 1e-7 cancels ~7 digits: the rounding of pow() is then ~1e-9 of the
+       * difference, differs between pow() implementations (glibc, XLA, CUDA) and is amplified by the
+       * shooting problem.  LITERAL IS THE DEFAULT (p[7] == 0); p[7] != 0 forms the VALUE of (1 - u)
+       * without cancellation, -expm1(log(Se)/m), every other term staying the literal expression
+       * (tests measure the gap between the two). */
+      int literal = (p[7] == 0.0);
       jet omu = j_sub(one, u);
-      if (!g_vg_literal) omu.v = -expm1(log(Se.v) / m);
-      jet h = j_scale(-1.0 / alpha, j_powc(g_vg_literal ? j_sub(j_recip(u), one) : j_div(omu, u), 1.0 / n));
+      if (!literal) omu.v = -expm1(log(Se.v) / m);
+      jet h = j_scale(-1.0 / alpha, j_powc(literal ? j_sub(j_recip(u), one) : j_div(omu, u), 1.0 / n));
       jet w = j_sub(one, j_powc(omu, m));
       jet kr = j_mul(j_powc(Se, l), j_mul(w, w));
       jet C = j_recip(j_deriv(h));
@@ -347,6 +351,9 @@ void fxo_default_options(fxo_options *opt) {
   opt->max_expansions = 64;
   opt->radial_k = 0;
   opt->ob = 0.0;
+  opt->u4_failure_aborts = 0;
+  opt->u5_or_termination = 0;
+  opt->u6_expand_rule = 0;
 }
 
 /* shoot(): one diffeqsolve with the boolean event (_forward.py:76-102) */
@@ -375,7 +382,15 @@ static shot_t shoot(int model, const double *p, double b, double i, double itol,
     int ok = kv5_attempt(&c, t0, h, y0, f0, y1, yerr, f7);
     n_attempts++;
     /* failed implicit solve or NaN error  =>  err = inf  (reject, shrink) */
-    if (!ok) { yerr[0] = INFINITY; yerr[1] = INFINITY; y1[0] = y0[0]; y1[1] = y0[1]; }
+    if (!ok) {
+      atomic_fetch_add(&g_diag[FXO_DIAG_STAGE_FAIL], 1);
+      /* U4: a failed implicit solve makes the attempt a REJECTED step (default, the only reading
+       * under which the reference's own known-answer tests pass -- tests/test_oracle_kat.py); the
+       * alternative reading ends the whole diffeqsolve without an event. */
+      if (opt->u4_failure_aborts) break;
+      yerr[0] = INFINITY; yerr[1] = INFINITY; y1[0] = y0[0]; y1[1] = y0[1];
+    }
+    if (isnan(yerr[0]) || isnan(yerr[1])) atomic_fetch_add(&g_diag[FXO_DIAG_NAN_ERROR], 1);
     if (isnan(yerr[0])) yerr[0] = INFINITY;
     if (isnan(yerr[1])) yerr[1] = INFINITY;
     /* PIDController (pcoeff=0, icoeff=1, dcoeff=0, safety 0.9, factormin 0.2, factormax 10) */
@@ -408,6 +423,7 @@ static shot_t shoot(int model, const double *p, double b, double i, double itol,
       }
     } else {
       n_rejected++;
+      if (ok) atomic_fetch_add(&g_diag[FXO_DIAG_ERROR_REJECT], 1);
     }
     t1 = t0 + dt_next;
   }
@@ -457,9 +473,13 @@ int fxo_solve(int model, const double *p, double b, double i, double itol, int m
   int result = 0;
   while (lo_neg == hi_neg) { /* expand_if_necessary (U6) */
     if (cnt[2] >= opt.max_expansions) { result = 2; break; }
+    /* U6: how optimistix widens the bracket is not verifiable here; rule 0 moves both ends out by
+     * the width (x3), rule 1 by half the width (x2), rule 2 moves the upper end only (x2) */
     double w = upper - lower;
-    lower -= w;
-    upper += w;
+    if (opt.u6_expand_rule == 1) { lower -= 0.5 * w; upper += 0.5 * w; }
+    else if (opt.u6_expand_rule == 2) { upper += w; }
+    else { lower -= w; upper += w; }
+    atomic_fetch_add(&g_diag[FXO_DIAG_EXPANSION], 1);
     last = shoot(model, p, b, i, itol, lower, &opt, k_max, knots, &nk, cnt);
     r_lo = last.residual;
     last = shoot(model, p, b, i, itol, upper, &opt, k_max, knots, &nk, cnt);
@@ -480,7 +500,10 @@ int fxo_solve(int model, const double *p, double b, double i, double itol, int m
       if ((res < 0.0) == lo_neg) lower = mid; else upper = mid;
       /* terminate: |upper-lower| < atol + rtol*|mid| (rtol = inf) AND |res| < atol */
       double scale = itol + INFINITY * fabs(mid);
-      if ((fabs(upper - lower) < scale) && (fabs(res) < itol)) { result = 0; break; }
+      /* U5: the two criteria are AND-ed (default).  OR-ed, rtol = inf makes the first one always
+       * true and the loop stops after one step, which fails tests/test_solve.py:42. */
+      int y_small = fabs(upper - lower) < scale, f_small = fabs(res) < itol;
+      if (opt.u5_or_termination ? (y_small || f_small) : (y_small && f_small)) { result = 0; break; }
     }
   }
   cnt[0] = result;

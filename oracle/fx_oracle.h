@@ -40,7 +40,7 @@ enum {
   FXO_CONSTANT = 0,       /* p[0]=D0                                                  */
   FXO_POWER_LAW = 1,      /* D = a*theta^k + eps;   p = {a, k, eps}                   */
   FXO_BROOKS_COREY = 2,   /* p = {n, l, Ks, alpha, theta_r, theta_s}                  */
-  FXO_VAN_GENUCHTEN = 3,  /* p = {n, m, l, Ks, alpha, theta_r, theta_s}               */
+  FXO_VAN_GENUCHTEN = 3,  /* p = {n, m, l, Ks, alpha, theta_r, theta_s, form}         */
   FXO_LETXS = 4,          /* p = {Lw, Ew, Tw, Ls, Es, Ts, Ks, alpha, theta_r, theta_s} */
   FXO_LETD = 5,           /* p = {L, E, T, Dwt, theta_r, theta_s}                     */
   FXO_LOG = 6             /* D = c0 + c1*ln(theta); p = {c0, c1}  (Philip 1960 test)  */
@@ -62,13 +62,30 @@ typedef struct {
   int max_expansions;   /* bound on bracket expansions (U6)  */
   int radial_k;         /* 0 planar (reference); 1 cylindrical/polar, 2 spherical (fronts) */
   double ob;            /* start of integration (0 for the reference) */
+  /* Switches for the dependency semantics that cannot be verified without the reference's
+   * executable.  0 = the reading this oracle takes by default. */
+  int u4_failure_aborts;   /* U4: 1 = a failed implicit stage solve ends the shot (no event) instead of
+                              being a rejected step with dt <- 0.2 dt */
+  int u5_or_termination;   /* U5: 1 = Bisection stops when EITHER |upper-lower| < atol + rtol|y| OR
+                              |residual| < atol (default: both) */
+  int u6_expand_rule;      /* U6: bracket expansion: 0 both ends out by the width, 1 both ends out by
+                              half the width, 2 upper end out by the width */
 } fxo_options;
 
 void fxo_default_options(fxo_options *opt);
 
-/* van Genuchten only: 1 = form 1 - Se^(1/m) by the literal (cancelling) subtraction,
- * 0 (default) = cancellation-free value; see the comment in D_jet(). Process-global. */
-void fxo_set_vg_literal(int on);
+/* van Genuchten: params[7] == 0 (default) forms 1 - Se^(1/m) by the literal (cancelling)
+ * subtraction of models.py:245,253; params[7] != 0 forms the same value without cancellation.
+ * See the comment in D_jet(). */
+
+/* diagnostics summed over all solves since fxo_diag_reset(): how often each uncertain branch ran */
+enum { FXO_DIAG_STAGE_FAIL = 0, /* attempts whose implicit solve failed (U4 path)          */
+       FXO_DIAG_ERROR_REJECT,   /* attempts rejected by the error test (err >= 1)         */
+       FXO_DIAG_NAN_ERROR,      /* attempts with a NaN error estimate (turned into inf)   */
+       FXO_DIAG_EXPANSION,      /* bracket expansions (U6 path)                           */
+       FXO_NDIAG };
+void fxo_diag_reset(void);
+void fxo_diag_get(int64_t *out /*[FXO_NDIAG]*/);
 
 /* D, D', D'' from the reference DEFINITIONS by 3rd-order Taylor jets. out[3]. */
 void fxo_D(int model, const double *p, double theta, double *out);

@@ -31,6 +31,9 @@ class Options(C.Structure):
         ("max_expansions", C.c_int),
         ("radial_k", C.c_int),
         ("ob", C.c_double),
+        ("u4_failure_aborts", C.c_int),
+        ("u5_or_termination", C.c_int),
+        ("u6_expand_rule", C.c_int),
     ]
 
 
@@ -256,9 +259,26 @@ def inverse(o, theta):
     return rc, Dk, s1.value, s2.value
 
 
-def set_vg_literal(on: bool) -> None:
-    """van Genuchten: literal cancelling subtraction (True) or cancellation-free value (False, default)."""
-    lib().fxo_set_vg_literal(int(bool(on)))
+def vg_form(params, form: str) -> np.ndarray:
+    """Copy of a [n,12] parameter block with every van Genuchten row's form flag (column 7) set:
+    'literal' = the reference's cancelling subtraction (the default of the models), 'expm1' = the
+    same value without cancellation."""
+    out = np.array(params, dtype=np.float64, copy=True)
+    out[..., 7] = {"literal": 0.0, "expm1": 1.0}[form]
+    return out
+
+
+DIAG = ("stage_fail", "error_reject", "nan_error", "expansion")
+
+
+def diag_reset() -> None:
+    lib().fxo_diag_reset()
+
+
+def diag() -> dict:
+    out = np.zeros(len(DIAG), dtype=np.int64)
+    lib().fxo_diag_get(out.ctypes.data_as(C.POINTER(C.c_int64)))
+    return dict(zip(DIAG, (int(v) for v in out)))
 
 
 def num_threads() -> int:

@@ -130,8 +130,10 @@ def test_gpu_flowrate_bitwise_vs_twin(fxo):
         np.testing.assert_array_equal(summary.cpu().numpy()[ok], tw["summary"][ok])
         np.testing.assert_array_equal(summary.cpu().numpy()[~ok][:, [0, 1, 2, 5, 6, 7]],
                                       tw["summary"][~ok][:, [0, 1, 2, 5, 6, 7]])
-        if k_max:
-            np.testing.assert_array_equal(knots.cpu().numpy(), tw["knots"])
+        if k_max:  # the rows that are the last shot's (speculative shots write no knots; the accepted one is re-run)
+            g, w, nk = knots.cpu().numpy(), tw["knots"], tw["counters"][:, 7]
+            valid = np.arange(k_max)[None, :] < np.minimum(nk, k_max)[:, None]
+            np.testing.assert_array_equal(g[valid], w[valid])
     assert fx.solve_flowrate is not None
 
 

@@ -19,6 +19,7 @@ import json
 from pathlib import Path
 
 import numpy as np
+import parity_util as pu
 import pytest
 from conftest import B_PAPER, I_PAPER, mixed_sweep, paper_models, vg_sweep
 
@@ -34,6 +35,16 @@ CNT = ("result", "n_shots", "n_expansions", "n_attempts", "n_rejected", "n_rhs",
 
 def counters_of(cpu: dict) -> np.ndarray:
     return np.stack([cpu[k] for k in CNT], axis=1)
+
+
+def assert_knots_equal(got: np.ndarray, want: np.ndarray, n_knots: np.ndarray) -> None:
+    """Dense-output tables, bit for bit, over the rows that ARE the last shot's (rows beyond n_knots are
+    leftovers of whichever earlier shot wrote there; on the GPU speculative shots write none)."""
+    cap = got.shape[1]
+    valid = np.arange(cap)[None, :] < np.minimum(n_knots, cap)[:, None]
+    g, w = got[valid], want[valid]
+    assert np.array_equal(np.isnan(g), np.isnan(w))
+    np.testing.assert_array_equal(g[~np.isnan(w)].view(np.int64), w[~np.isnan(w)].view(np.int64))
 
 
 # ---------------------------------------------------------------------------
@@ -56,8 +67,17 @@ def test_diffusivity_vs_oracle_dense(fxo, paper):
         th = tr + (ts - tr) * np.concatenate([np.geomspace(1e-4, 0.5, 40), 1 - np.geomspace(2e-7, 0.5, 40)])
         got = m.derivatives(th)
         want = fxo.D(m.model_id, m.params(), th)
-        np.testing.assert_allclose(got, want, rtol=2e-11, err_msg=name)
+        # van Genuchten's default is the reference's literal 1 - Se**(1/m): exp(log) and pow round Se^(1/m)
+        # differently, ~1e-16/(1 - Se^(1/m)) of D -- 2e-11 away from saturation, ~1e-9 at theta_s - 1e-7
+        tol = 2e-11 + (4e-16 / (1.0 - (th - tr) / (ts - tr)) if isinstance(m, M.VanGenuchten) else 0.0)
+        assert (np.abs(got / want - 1) <= 3 * np.broadcast_to(tol, th.shape)[:, None]).all(), name
         np.testing.assert_array_equal(got, fxo.twin_D(m.model_id, m.params(), th), err_msg=name)  # bit for bit
+        if isinstance(m, M.VanGenuchten):  # the cancellation-free form agrees with the jets to 2e-11 everywhere
+            import dataclasses
+
+            mf = dataclasses.replace(m, form="expm1")
+            np.testing.assert_allclose(mf.derivatives(th), fxo.D(mf.model_id, mf.params(), th), rtol=2e-11)
+            np.testing.assert_array_equal(mf.derivatives(th), fxo.twin_D(mf.model_id, mf.params(), th))
     for m, th in ((fx.D.power_law(k=4), np.linspace(0.05, 1.2, 30)),
                   (fx.D.power_law(k=2.5, a=3.0, epsilon=0.1), np.linspace(0.05, 1.2, 30)),
                   (fx.D.philip_exact(), np.linspace(1e-6, 1.0, 30)), (fx.D.constant(2.5), np.linspace(0, 1, 5))):
@@ -118,7 +138,7 @@ def test_paper_sets_bitwise_vs_twin(solved_cases):
     cases, gpu, _, twin = solved_cases
     np.testing.assert_array_equal(gpu.counters.cpu().numpy(), twin["counters"])
     np.testing.assert_array_equal(gpu.summary.cpu().numpy(), twin["summary"])
-    np.testing.assert_array_equal(gpu.knots.cpu().numpy(), twin["knots"])
+    assert_knots_equal(gpu.knots.cpu().numpy(), twin["knots"], twin["counters"][:, 7])
 
 
 def test_paper_sets_step_sequence_vs_literal(solved_cases):
@@ -142,31 +162,55 @@ def test_paper_sets_step_sequence_vs_literal(solved_cases):
     assert len(differing) <= 1, differing
 
 
-def test_paper_sets_summary(solved_cases):
+@pytest.fixture(scope="module")
+def case_conditioning(fxo, solved_cases):
+    """Per case: how far the literal oracle's own profile moves when b or a parameter moves by one ulp."""
+    cases, _, ref, _ = solved_cases
+    models = fx.ModelBatch.from_models([c[1] for c in cases])
+    b = np.array([c[2] for c in cases])
+    i = np.array([c[3] for c in cases])
+    _, self_dev = pu.conditioning(fxo, models.model_id, models.params, b, i, ref, 512)
+    return self_dev.max(axis=0)
+
+
+def test_paper_sets_summary(solved_cases, case_conditioning):
     cases, gpu, ref, _ = solved_cases
     g = gpu.cpu()
     s = ref["summary"]
-    np.testing.assert_allclose(g["d_dob"], s[:, 0], rtol=1e-13)  # same bisection midpoints
-    np.testing.assert_allclose(g["i"], s[:, 2], rtol=1e-6)
-    np.testing.assert_allclose(g["sorptivity"], s[:, 3], rtol=1e-6)
-    np.testing.assert_allclose(g["D_b"], s[:, 4], rtol=1e-11)
-    np.testing.assert_allclose(g["residual"], s[:, 5], rtol=1e-3, atol=1e-8)
-    # oi is where the numerical tail happens to end (error estimates there are rounding noise)
-    np.testing.assert_allclose(g["oi"], s[:, 1], rtol=1e-4)
-
-
-def test_paper_sets_profiles(fxo, solved_cases):
-    cases, gpu, ref, _ = solved_cases
+    np.testing.assert_allclose(g["d_dob"], s[:, 0], rtol=1e-9)  # same bisection midpoints (D(b) scales the bracket)
+    np.testing.assert_allclose(g["sorptivity"], s[:, 3], rtol=1e-8)
+    np.testing.assert_allclose(g["D_b"], s[:, 4], rtol=3e-9)    # literal 1 - Se^(1/m) at theta_s - 1e-7: exp(log) vs pow
+    np.testing.assert_allclose(g["residual"], s[:, 5], rtol=1e-3, atol=2e-7)
+    # the achieved far-field value and oi (where the numerical tail happens to end: the error estimates there
+    # are rounding noise) are as well defined as the oracle's own profile is under a one-ulp change of its inputs
     for j, c in enumerate(cases):
+        tol = max(1e-6, 30 * case_conditioning[j])
+        assert abs(g["i"][j] / s[j, 2] - 1) < tol, (c[0], g["i"][j], s[j, 2], case_conditioning[j])
+        assert abs(g["oi"][j] / s[j, 1] - 1) < max(1e-4, 100 * case_conditioning[j]), c[0]
+
+
+def test_paper_sets_profiles(fxo, solved_cases, case_conditioning):
+    """theta(o), d theta/do and the sorptivity along the profile within 1e-6 / 1e-5 of the literal oracle --
+    or, for the van Genuchten sets at b = theta_s - 1e-7, within what the oracle's own profile moves by when
+    one input moves by one ulp (printed)."""
+    cases, gpu, ref, _ = solved_cases
+    rec = pu.as_record(gpu)
+    dev = pu.profile_deviation(fxo, rec, ref, npts=300)
+    print("\n" + ", ".join(f"{c[0]}: {d:.1e} (oracle self {s:.1e})" for c, d, s in zip(cases, dev, case_conditioning)))
+    for j, c in enumerate(cases):
+        slack = max(1.0, 30 * case_conditioning[j] / 1e-6)
+        assert dev[j] < 1e-6 * slack, (c[0], dev[j], case_conditioning[j])
         nk = int(ref["counters"][j, 7])
-        o = np.linspace(0, ref["summary"][j, 1], 300)
+        o = np.linspace(0, min(ref["summary"][j, 1], rec["summary"][j, 1]), 300)
         th_c, dth_c = fxo.evaluate(ref["knots"][j, :nk], o)
         sol = gpu[j]
-        np.testing.assert_allclose(sol(o), th_c, rtol=1e-6, err_msg=c[0])
-        np.testing.assert_allclose(sol.d_do(o), dth_c, rtol=1e-5, atol=1e-6 * np.abs(dth_c).max(), err_msg=c[0])
+        np.testing.assert_allclose(sol(o), th_c, rtol=1e-6 * slack, err_msg=c[0])
+        np.testing.assert_allclose(sol.d_do(o), dth_c, rtol=1e-5 * slack, atol=1e-6 * slack * np.abs(dth_c).max(),
+                                   err_msg=c[0])
         # sorptivity along the profile: -2 D(theta) dtheta/do  (_boltzmann.py:158-161)
         S_c = -2 * fxo.D(c[1].model_id, c[1].params(), th_c)[:, 0] * dth_c
-        np.testing.assert_allclose(sol.sorptivity(o), S_c, rtol=1e-5, atol=1e-6 * np.abs(S_c).max(), err_msg=c[0])
+        np.testing.assert_allclose(sol.sorptivity(o), S_c, rtol=1e-5 * slack, atol=1e-6 * slack * np.abs(S_c).max(),
+                                   err_msg=c[0])
 
 
 def test_reference_test_exact():
@@ -207,69 +251,127 @@ def test_reference_test_fronts_papers(fxo, paper, name):
 # ---------------------------------------------------------------------------
 # sweeps: BASELINE configs C2 and C3 at oracle-sized batches
 # ---------------------------------------------------------------------------
-def compare_sweep(fxo, models):
-    """GPU vs twin: bit for bit.  GPU vs literal oracle: statistics of the 1e-6 criterion."""
-    gpu = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
-    twin = fxo.twin_solve_batch(models.model_id, models.params, B_PAPER, I_PAPER)
-    np.testing.assert_array_equal(gpu.counters.cpu().numpy(), twin["counters"])
-    np.testing.assert_array_equal(gpu.summary.cpu().numpy(), twin["summary"])
-    ref = fxo.solve_batch(models.model_id, models.params, B_PAPER, I_PAPER)
-    g = gpu.cpu()
-    got = counters_of(g)
-    seq = [0, 1, 2, 3, 4, 6, 7]  # everything but n_rhs
-    same = (got[:, seq] == ref["counters"][:, seq]).all(axis=1)
-    s = ref["summary"]
-    rel_d = np.abs(g["d_dob"] / s[:, 0] - 1)
-    rel_S = np.abs(g["sorptivity"] / s[:, 3] - 1)
-    rel_i = np.abs(g["i"] / s[:, 2] - 1)
-    return {"same": same, "rel_d": rel_d, "rel_S": rel_S, "rel_i": rel_i,
-            "shots_equal": got[:, 1] == ref["counters"][:, 1],
-            "result_equal": got[:, 0] == ref["counters"][:, 0], "gpu": g, "ref": ref}
+def compare_sweep(fxo, models, label):
+    """GPU vs twin: bit for bit.  GPU vs literal oracle: theta(o) on 128 points and the sorptivity per problem,
+    with the conditioning control of tests/parity_util.py; returns what the assertions need."""
+    gpu = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=512, throw=False)
+    rec = pu.as_record(gpu)
+    twin = fxo.twin_solve_batch(models.model_id, models.params, B_PAPER, I_PAPER, k_max=512)
+    np.testing.assert_array_equal(rec["counters"], twin["counters"])
+    np.testing.assert_array_equal(rec["summary"], twin["summary"])
+    assert_knots_equal(rec["knots"], twin["knots"], twin["counters"][:, 7])
+    lean = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)  # summaries only: same numbers
+    np.testing.assert_array_equal(lean.summary.cpu().numpy(), rec["summary"])
+    np.testing.assert_array_equal(lean.counters.cpu().numpy(), rec["counters"])
+    fxo.diag_reset()
+    ref = fxo.solve_batch(models.model_id, models.params, B_PAPER, I_PAPER, k_max=512)
+    diag = fxo.diag()
+    same = pu.same_decisions(rec, ref)
+    dev = pu.profile_deviation(fxo, rec, ref)
+    rel_S = np.abs(rec["summary"][:, 3] / ref["summary"][:, 3] - 1)
+    names, self_dev = pu.conditioning(fxo, models.model_id, models.params, B_PAPER, I_PAPER, ref, 512)
+    print("\n" + pu.report(f"{label}: GPU vs literal oracle", dev, rel_S, same, names, self_dev))
+    print(f"    oracle branches: {diag}")
+    return {"same": same, "dev": dev, "rel_S": rel_S, "self_dev": self_dev, "rec": rec, "ref": ref, "diag": diag}
 
 
-def test_vg_sweep_parity(fxo):
-    """C2 at N=3000.  Bitwise equal to the twin; against the literal oracle the sorptivity
-    (= -2 D(b) d_dob, a bisection midpoint) agrees to 1e-6 wherever the bisection took the
-    same path, the far-field value wherever the step sequences coincide and theta(oi) is not
-    dominated by the fp64 rounding of theta next to saturation (reported, bounded)."""
-    r = compare_sweep(fxo, vg_sweep(3000))
-    print(f"\nVG sweep vs literal oracle: same step sequence {r['same'].mean():.4f}, same shots "
-          f"{r['shots_equal'].mean():.4f}, same status {r['result_equal'].mean():.4f}, sorptivity within 1e-6 "
-          f"{(r['rel_S'] < 1e-6).mean():.4f}, theta(oi) within 1e-6 {(r['rel_i'] < 1e-6).mean():.4f}")
-    assert r["same"].mean() >= 0.97
-    assert r["shots_equal"].mean() >= 0.99 and r["result_equal"].mean() >= 0.995
-    assert (r["rel_S"] < 1e-6).mean() >= 0.99
-    assert (r["rel_i"] < 1e-6).mean() >= 0.90
-    assert (r["rel_i"] < 1e-3).mean() >= 0.995
-    assert (r["gpu"]["n_expansions"] == 0).all()
+def assert_explained(r, min_same):
+    rec, ref, dev, same, self_dev = r["rec"], r["ref"], r["dev"], r["same"], r["self_dev"]
+    assert r["diag"]["expansion"] == 0 and (rec["counters"][:, 2] == 0).all()   # U6 never reached
+    assert (rec["counters"][:, 0] == ref["counters"][:, 0]).all()               # same status, every problem
+    assert (rec["counters"][:, 1] == ref["counters"][:, 1]).mean() >= 0.99       # shooting iterations
+    assert same.mean() >= min_same
+    # every problem outside 1e-6 took a different discrete decision or is one the oracle itself does not
+    # reproduce to 1e-7 when one of its inputs moves by one ulp
+    unexplained = (dev >= 1e-6) & same & ~(self_dev.max(axis=0) >= 1e-7)
+    assert not unexplained.any(), np.where(unexplained)[0][:10]
+    worst_self = min((d < 1e-6).mean() for d in self_dev)
+    assert (dev < 1e-6).mean() >= worst_self - 0.03, ((dev < 1e-6).mean(), worst_self)
+    assert np.percentile(dev, 99) <= 10 * max(np.percentile(d, 99) for d in self_dev)
+    assert (r["rel_S"][same] < 1e-6).all() and (r["rel_S"] < 1e-6).mean() >= 0.99
+
+
+@pytest.mark.parametrize("form", ["literal", "expm1"])
+def test_vg_sweep_parity(fxo, form):
+    """C2 at N=3000, both forms of 1 - Se^(1/m) (the reference's literal subtraction is the default).  Bitwise
+    equal to the twin; against the literal oracle every deviation beyond 1e-6 is explained (parity_util)."""
+    mb = vg_sweep(3000)
+    mb = fx.ModelBatch(mb.model_id, fxo.vg_form(mb.params, form))
+    assert_explained(compare_sweep(fxo, mb, f"C2 van Genuchten sweep, {form}"), 0.95)
 
 
 def test_mixed_sweep_parity(fxo):
     """C3 at N=3000: Brooks-Corey / LETd interleaved, bucketed by model on the device."""
-    r = compare_sweep(fxo, mixed_sweep(3000))
-    print(f"\nmixed sweep vs literal oracle: same step sequence {r['same'].mean():.4f}, sorptivity within 1e-6 "
-          f"{(r['rel_S'] < 1e-6).mean():.4f}, theta(oi) within 1e-6 {(r['rel_i'] < 1e-6).mean():.4f}")
-    assert r["same"].mean() >= 0.95
-    assert r["result_equal"].mean() >= 0.995
-    assert (r["rel_S"] < 1e-6).mean() >= 0.99
-    assert (r["rel_i"] < 1e-6).mean() >= 0.97
+    r = compare_sweep(fxo, mixed_sweep(3000), "C3 mixed Brooks-Corey / LETd")
+    assert_explained(r, 0.95)
+    assert (r["dev"] < 1e-6).mean() >= 0.97
 
 
 # ---------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------
-def test_speculative_and_sequential_bisection_agree(fxo):
-    """With k_max = 0 idle lanes run the bisection tree speculatively (a few thousand problems on 95 000
-    lanes: depth 5 from the first midpoint); with dense output requested every shot is sequential.
-    Same summaries, same counters (only shots on the taken path are counted), equal to the twin's."""
+def test_with_and_without_dense_output_agree(fxo):
+    """A few thousand problems on 95 000 lanes: idle lanes run the bisection tree speculatively (depth 5 from
+    the first midpoint).  Speculative shots write no knots; with dense output requested the accepted shot is
+    integrated once more for them.  Same summaries, same counters (only shots on the taken path are counted),
+    equal to the twin's, and the knot tables are the twin's last shot."""
     mb = vg_sweep(3000, seed=11)
-    spec = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
-    seq = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=8, throw=False)
-    np.testing.assert_array_equal(spec.summary.cpu().numpy(), seq.summary.cpu().numpy())
-    np.testing.assert_array_equal(spec.counters.cpu().numpy(), seq.counters.cpu().numpy())
-    tw = fxo.twin_solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER)
-    np.testing.assert_array_equal(spec.summary.cpu().numpy(), tw["summary"])
-    np.testing.assert_array_equal(spec.counters.cpu().numpy(), tw["counters"])
+    lean = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    dense = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=160, throw=False)
+    np.testing.assert_array_equal(lean.summary.cpu().numpy(), dense.summary.cpu().numpy())
+    np.testing.assert_array_equal(lean.counters.cpu().numpy(), dense.counters.cpu().numpy())
+    tw = fxo.twin_solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER, k_max=160)
+    np.testing.assert_array_equal(lean.summary.cpu().numpy(), tw["summary"])
+    np.testing.assert_array_equal(lean.counters.cpu().numpy(), tw["counters"])
+    assert_knots_equal(dense.knots.cpu().numpy(), tw["knots"], tw["counters"][:, 7])
+    one = fx.ModelBatch(mb.model_id[:1], mb.params[:1])  # a single problem speculates from its first midpoint
+    solo = fx.solve_batch(one, b=B_PAPER, i=I_PAPER, k_max=160, throw=False)
+    np.testing.assert_array_equal(solo.summary.cpu().numpy(), tw["summary"][:1])
+    assert_knots_equal(solo.knots.cpu().numpy(), tw["knots"][:1], tw["counters"][:1, 7])
+
+
+def test_model_mask_hint():
+    """opt->model_mask: only the models named get a launch; a problem outside the mask is flagged, not solved."""
+    mb = mixed_sweep(64)
+    full = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    hinted = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False,
+                            options={"model_mask": (1 << _lib.BROOKS_COREY) | (1 << _lib.LETD)})
+    np.testing.assert_array_equal(full.summary.cpu().numpy(), hinted.summary.cpu().numpy())
+    partial = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False, options={"model_mask": 1 << _lib.LETD})
+    c = partial.counters.cpu().numpy()
+    assert (c[mb.model_id == _lib.BROOKS_COREY, 0] == -1).all() and (c[mb.model_id == _lib.LETD, 0] == 0).all()
+    np.testing.assert_array_equal(partial.summary.cpu().numpy()[mb.model_id == _lib.LETD],
+                                  full.summary.cpu().numpy()[mb.model_id == _lib.LETD])
+
+
+def test_two_host_threads_two_streams(fxo):
+    """fx_solve_batch is re-entrant: two host threads on two streams of one device get the results each gets
+    alone (per-stream fork sets; the round-1 library shared one set of helper events per device)."""
+    import threading
+
+    import torch
+
+    a, b_ = vg_sweep(6000, seed=31), mixed_sweep(6000, seed=32)
+    want = [fx.solve_batch(m, b=B_PAPER, i=I_PAPER, k_max=0, throw=False).summary.cpu().numpy() for m in (a, b_)]
+    for _ in range(3):
+        out, err = [None, None], []
+
+        def work(k, models):
+            try:
+                with torch.cuda.stream(torch.cuda.Stream()):
+                    for _ in range(3):
+                        out[k] = fx.solve_batch(models, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+                    torch.cuda.current_stream().synchronize()
+            except Exception as exc:  # noqa: BLE001
+                err.append(exc)
+
+        th = [threading.Thread(target=work, args=(k, m)) for k, m in enumerate((a, b_))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not err, err
+        torch.cuda.synchronize()
+        for k in range(2):
+            np.testing.assert_array_equal(out[k].summary.cpu().numpy(), want[k])
 
 
 def test_all_models_random_batch_bitwise_vs_twin(fxo):
@@ -315,7 +417,7 @@ def test_all_models_random_batch_bitwise_vs_twin(fxo):
         got, want = sol.summary.cpu().numpy(), tw["summary"]
         assert np.array_equal(np.isnan(got), np.isnan(want))
         np.testing.assert_array_equal(got[~np.isnan(want)].view(np.int64), want[~np.isnan(want)].view(np.int64))
-    np.testing.assert_array_equal(seq.knots.cpu().numpy(), tw["knots"])
+    assert_knots_equal(seq.knots.cpu().numpy(), tw["knots"], tw["counters"][:, 7])
 
 
 def test_empty_and_single():

@@ -37,16 +37,16 @@ def test_diffusivity_golden(fxo, paper, name):
 
 
 def test_diffusivity_vg_literal_noise(fxo, paper):
-    """The literal 1 - Se**(1/m) carries ~1e-10 relative noise at b = theta_s - 1e-7."""
+    """The literal 1 - Se**(1/m) (the models' default, as the reference writes it) carries ~1e-10 relative
+    noise at b = theta_s - 1e-7; the cancellation-free form (params[7] = 1) does not."""
     m = paper["VG(n)"]
     row = GOLDEN["sets"]["VG(n)"]["values"]["b=0.7-1e-7"]
-    fxo.set_vg_literal(True)
-    try:
-        lit = fxo.D(m.model_id, m.params(), [row["theta"]])[0, 0]
-    finally:
-        fxo.set_vg_literal(False)
+    assert m.params()[7] == 0.0  # literal by default
+    lit = fxo.D(m.model_id, m.params(), [row["theta"]])[0, 0]
+    free = fxo.D(m.model_id, fxo.vg_form(m.params(), "expm1"), [row["theta"]])[0, 0]
     rel = abs(lit / float(row["D"]) - 1)
     assert 1e-13 < rel < 5e-9  # noisy, but within the reference's own rel 1e-6 check
+    assert abs(free / float(row["D"]) - 1) < 3e-9  # what is left is the rounding of b itself
 
 
 def test_philip_exact(fxo):

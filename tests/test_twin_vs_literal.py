@@ -15,6 +15,7 @@ from pathlib import Path
 
 import numpy as np
 import pytest
+import parity_util as pu
 from conftest import B_PAPER, I_PAPER, mixed_sweep, vg_sweep
 
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "diffusivity_golden.json").read_text())
@@ -51,50 +52,111 @@ def test_kernel_diffusivity_vs_golden_and_literal(fxo, paper, name):
         np.testing.assert_allclose(got, want, rtol=rtol, err_msg=f"{name} @ {pname}")
     tr, ts = m.theta_range
     th = tr + (ts - tr) * np.concatenate([np.geomspace(1e-4, 0.5, 60), 1 - np.geomspace(2e-7, 0.5, 60)])
-    np.testing.assert_allclose(fxo.twin_D(m.model_id, m.params(), th), fxo.D(m.model_id, m.params(), th),
-                               rtol=2e-11, err_msg=name)
+    # cancellation-free form of 1 - Se^(1/m) on both sides: closed forms vs jets to 2e-11 everywhere
+    pf = fxo.vg_form(m.params(), "expm1")
+    np.testing.assert_allclose(fxo.twin_D(m.model_id, pf, th), fxo.D(m.model_id, pf, th), rtol=2e-11, err_msg=name)
+    # the reference's literal subtraction (the default): exp(log)/pow round Se^(1/m) differently, which is
+    # ~1e-16/(1 - Se^(1/m)) of D, D', D'' -- 2e-11 away from saturation, ~1e-9 at theta_s - 1e-7
+    got, want = fxo.twin_D(m.model_id, m.params(), th), fxo.D(m.model_id, m.params(), th)
+    tol = 2e-11 + 4e-16 / (1.0 - (th - tr) / (ts - tr))
+    assert (np.abs(got / want - 1) <= 3 * tol[:, None]).all(), name
 
 
 def test_paper_sets_twin_vs_literal(fxo, paper):
+    """The six parameter sets of the reference's tests: bisection path, status and accepted d_dob equal the
+    literal oracle's; theta(o) agrees to 1e-6 wherever the oracle's own profile is that well defined (for
+    each set the oracle is also run with b and two parameters moved by one ulp: where IT moves by more
+    than 1e-7, two roundings of D cannot be asked to agree to 1e-6)."""
     ms = list(paper.values())
     ids = np.array([m.model_id for m in ms], dtype=np.int32)
     par = np.stack([m.params() for m in ms])
-    tw = fxo.twin_solve_batch(ids, par, B_PAPER, I_PAPER, k_max=512)
-    lit = fxo.solve_batch(ids, par, B_PAPER, I_PAPER, k_max=512)
-    seq = [0, 1, 2, 3, 4, 6, 7]  # status, shots, expansions, attempts, rejected, Jacobians, knots
-    # The accept/reject sequence of a shot is chaotic in the last bits of D (module docstring): the
-    # two implementations take the same decisions in all but at most one of the six sets, and the
-    # bisection (shots, status), the accepted d_dob and the final shot's knot count agree in all six.
-    same = (tw["counters"][:, seq] == lit["counters"][:, seq]).all(axis=1)
-    assert same.sum() >= len(ms) - 1
-    np.testing.assert_array_equal(tw["counters"][:, [0, 1, 2, 7]], lit["counters"][:, [0, 1, 2, 7]])
-    np.testing.assert_allclose(tw["summary"][:, 0], lit["summary"][:, 0], rtol=1e-13)  # d_dob
-    np.testing.assert_allclose(tw["summary"][:, 3], lit["summary"][:, 3], rtol=1e-9)   # sorptivity
-    np.testing.assert_allclose(tw["summary"][:, 2], lit["summary"][:, 2], rtol=1e-6)   # theta(oi)
-    for j in range(len(ms)):
-        nk = int(lit["counters"][j, 7])
-        o = np.linspace(0, lit["summary"][j, 1], 200)
-        th_l, _ = fxo.evaluate(lit["knots"][j, :nk], o)
-        k4 = tw["knots"][j, :nk]
-        k5 = np.concatenate([k4[:, :3], k4[:, 2:3], k4[:, 3:4]], axis=1)  # (o, th, p, F0=p, F1)
-        th_t, _ = fxo.evaluate(k5, o)
-        np.testing.assert_allclose(th_t, th_l, rtol=1e-6)
+    for form in ("literal", "expm1"):
+        p = fxo.vg_form(par, form)
+        tw = fxo.twin_solve_batch(ids, p, B_PAPER, I_PAPER, k_max=512)
+        lit = fxo.solve_batch(ids, p, B_PAPER, I_PAPER, k_max=512)
+        same = pu.same_decisions(tw, lit)
+        # the accept/reject sequence inside the shots is chaotic in the last bits of D: all but at most one
+        # set take the same decisions; shots, status and the final shot's knot count agree in all six
+        assert same.sum() >= len(ms) - 1, form
+        np.testing.assert_array_equal(tw["counters"][:, [0, 1, 2, 7]], lit["counters"][:, [0, 1, 2, 7]])
+        np.testing.assert_allclose(tw["summary"][:, 0], lit["summary"][:, 0], rtol=1e-9)   # d_dob: same midpoints
+        np.testing.assert_allclose(tw["summary"][:, 3], lit["summary"][:, 3], rtol=1e-8)   # sorptivity
+        dev = pu.profile_deviation(fxo, tw, lit)
+        names, self_dev = pu.conditioning(fxo, ids, p, B_PAPER, I_PAPER, lit, 512)
+        print("\n" + form + ": " + ", ".join(f"{k} {d:.1e} (oracle self {s:.1e})"
+                                             for k, d, s in zip(paper, dev, self_dev.max(axis=0))))
+        for k, d, s, sm in zip(paper, dev, self_dev.max(axis=0), same):
+            assert d < 1e-6 or s >= 1e-7 or not sm, (form, k, d, s)
+            assert d < 5e-5, (form, k, d)
 
 
-@pytest.mark.parametrize("which", ["vg", "mixed"])
-def test_sweep_twin_vs_literal_statistics(fxo, which):
-    """How much of the 1e-6 criterion survives a different pow()/fma: reported and bounded."""
-    mb = vg_sweep(1200) if which == "vg" else mixed_sweep(1200)
-    tw = fxo.twin_solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER)
-    lit = fxo.solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER)
-    seq = [0, 1, 2, 3, 4, 6, 7]
-    same = (tw["counters"][:, seq] == lit["counters"][:, seq]).all(axis=1)
+@pytest.mark.parametrize("which,form", [("vg", "literal"), ("vg", "expm1"), ("mixed", "literal")])
+def test_sweep_twin_vs_literal_explained(fxo, which, form):
+    """BASELINE configs C2 / C3 at oracle size.  theta(o) on 128 points and the sorptivity, per problem,
+    product arithmetic (twin) vs the literal oracle; the exact fractions within 1e-6 are printed.  What
+    lies outside is EXPLAINED: every such problem took a different discrete decision somewhere or is one
+    the literal oracle itself does not reproduce to 1e-7 when one of its inputs moves by one ulp -- and the
+    product is as close to the oracle as the oracle is to itself under those perturbations."""
+    n = 1200
+    mb = vg_sweep(n) if which == "vg" else mixed_sweep(n)
+    par = fxo.vg_form(mb.params, form) if which == "vg" else mb.params
+    fxo.diag_reset()
+    lit = fxo.solve_batch(mb.model_id, par, B_PAPER, I_PAPER, k_max=512)
+    diag = fxo.diag()
+    tw = fxo.twin_solve_batch(mb.model_id, par, B_PAPER, I_PAPER, k_max=512)
+    same = pu.same_decisions(tw, lit)
+    dev = pu.profile_deviation(fxo, tw, lit)
     rel_S = np.abs(tw["summary"][:, 3] / lit["summary"][:, 3] - 1)
-    rel_i = np.abs(tw["summary"][:, 2] / lit["summary"][:, 2] - 1)
-    print(f"\n{which}: same step sequence {same.mean():.4f}; sorptivity within 1e-6 {(rel_S < 1e-6).mean():.4f}; "
-          f"theta(oi) within 1e-6 {(rel_i < 1e-6).mean():.4f}, within 1e-3 {(rel_i < 1e-3).mean():.4f}")
-    assert (tw["counters"][:, 0] == lit["counters"][:, 0]).mean() >= 0.995  # same status
+    names, self_dev = pu.conditioning(fxo, mb.model_id, par, B_PAPER, I_PAPER, lit, 512)
+    print("\n" + pu.report(f"{which}/{form} twin vs literal oracle", dev, rel_S, same, names, self_dev))
+    print(f"    oracle branches: {diag}")
+    # the uncertain dependency semantics this distribution exercises: never the bracket expansion (U6)
+    assert diag["expansion"] == 0 and (lit["counters"][:, 2] == 0).all() and (tw["counters"][:, 2] == 0).all()
+    assert (tw["counters"][:, 0] == lit["counters"][:, 0]).all()          # same status, every problem
+    assert (tw["counters"][:, 1] == lit["counters"][:, 1]).mean() >= 0.99  # same number of shots
     assert same.mean() >= 0.95
+    # explained, not tolerated
+    bad = dev >= 1e-6
+    ill = self_dev.max(axis=0) >= 1e-7
+    unexplained = bad & same & ~ill
+    assert not unexplained.any(), np.where(unexplained)[0][:10]
+    # as close to the oracle as the oracle is to itself one ulp away
+    worst_self = min((d < 1e-6).mean() for d in self_dev)
+    assert (dev < 1e-6).mean() >= worst_self - 0.03, ((dev < 1e-6).mean(), worst_self)
+    assert np.percentile(dev, 99) <= 10 * max(np.percentile(d, 99) for d in self_dev)
+    # sorptivity = -2 D(b) d_dob with d_dob a bisection midpoint: 1e-6 wherever the bisection took the same path
+    assert (rel_S[same] < 1e-6).all()
     assert (rel_S < 1e-6).mean() >= 0.99
-    assert (rel_i < 1e-6).mean() >= (0.90 if which == "vg" else 0.97)
-    assert (rel_i < 1e-3).mean() >= 0.995
+
+
+def test_uncertain_dependency_semantics_are_pinned_or_unreached(fxo):
+    """SURVEY.md Appendix A marks three behaviours of diffrax/optimistix as not verifiable here.  Each is
+    a switch of the oracle; this test bounds what a wrong guess could cost.
+      U4 (a failed implicit stage solve = a rejected step): the other reading ends the shot, and then the
+         reference's own analytic test (tests/test_solve.py:38-42, exp(-o) to 1e-3) cannot pass;
+      U5 (Bisection stops when BOTH criteria hold): OR-ed, rtol = inf stops after one step; same test fails;
+      U6 (how the bracket is widened): exercised by the Philip and constant-D cases only (never by the
+         benchmark distributions, see test_sweep_twin_vs_literal_explained); the rules differ by < itol there."""
+    o = np.linspace(0, 20, 100)
+
+    def philip(**kw):
+        r = fxo.solve(fxo.LOG, [0.5, -0.5], b=1.0, i=0.0, options=fxo.default_options(**kw))
+        th, _ = fxo.evaluate(r["knots"], o) if len(r["knots"]) else (np.full(o.shape, np.nan), None)
+        return r, float(np.nanmax(np.abs(th - np.exp(-o)))) if np.isfinite(th).any() else np.inf
+
+    base, err = philip()
+    assert base["counters"][0] == 0 and err < 1e-3 and base["counters"][2] >= 1  # passes, and needs an expansion
+    fxo.diag_reset()
+    philip()
+    assert fxo.diag()["stage_fail"] > 0  # the U4 path is taken in the reference's own test case ...
+    r4, err4 = philip(u4_failure_aborts=1)
+    assert r4["counters"][0] != 0 or not err4 < 1e-3  # ... and the other reading fails that test
+    r5, err5 = philip(u5_or_termination=1)
+    assert not err5 < 1e-3
+    for rule in (1, 2):
+        r6, err6 = philip(u6_expand_rule=rule)
+        assert r6["counters"][0] == 0 and err6 < 1e-3  # every rule passes the reference's test ...
+        assert abs(r6["summary"][0] - base["summary"][0]) < 1e-3  # ... within itol of each other
+    # the paper sets and the C1 power law never expand
+    r = fxo.solve(fxo.POWER_LAW, [1.0, 4.0, 0.0], b=1.0, i=0.1)
+    assert r["counters"][2] == 0
