@@ -12,7 +12,7 @@ from . import D, models
 from ._forward import (RESULTS, BatchSolution, Solution, SolveError, solve, solve_batch, solve_batch_host,
                        solve_flowrate, solve_flowrate_batch)
 from ._fit import Param, ScaledSolution, fit
-from ._inverse import BatchInverse, InterpolatedSolution, inverse, sorptivity
+from ._inverse import BatchInverse, InterpolatedSolution, inverse, sorptivity, unique_profile
 from ._lib import FrontxB200Error
 from .models import ModelBatch
 
@@ -39,4 +39,5 @@ __all__ = [
     "solve_flowrate",
     "solve_flowrate_batch",
     "sorptivity",
+    "unique_profile",
 ]

@@ -36,64 +36,98 @@ def shard_sizes(n: int, world: int, block: int = BLOCK) -> np.ndarray:
     return np.array([shard_indices(n, r, world, block).size for r in range(world)], dtype=np.int64)
 
 
-def gather_records(local, n: int, world: int, rank: int, block: int = BLOCK, group: Any = None):
+def gather_order(n: int, world: int, block: int = BLOCK) -> np.ndarray:
+    """Global problem index of every row of the padded all-gather buffer (``world`` shards of the largest
+    shard's size, rank-major), -1 for padding rows."""
+    sizes = shard_sizes(n, world, block)
+    pad = int(sizes.max()) if sizes.size else 0
+    order = np.full(world * pad, -1, dtype=np.int64)
+    for r in range(world):
+        order[r * pad: r * pad + int(sizes[r])] = shard_indices(n, r, world, block)
+    return order
+
+
+def gather_records(local, n: int, world: int, rank: int, block: int = BLOCK, group: Any = None, order=None):
     """All-gather per-problem records ([n_local, w] tensors) into global order [n, w].
 
-    Shards are padded to the largest shard so that one ``all_gather_into_tensor``
-    moves everything (64-byte summaries: 640 MB at n = 1e7, ~1 ms over NVSwitch).
+    Shards are padded to the largest shard so that ONE ``all_gather_into_tensor`` moves everything
+    (64-byte summaries: 640 MB at n = 1e7, ~1 ms over NVSwitch), and ONE indexed copy puts the rows in
+    the caller's order (``order`` = ``gather_order(n, world, block)`` as a tensor on the records' device;
+    pass it to reuse it across calls).
     """
     import torch
     import torch.distributed as dist
 
-    sizes = shard_sizes(n, world, block)
-    pad = int(sizes.max()) if sizes.size else 0
-    width = local.shape[1]
-    send = torch.zeros((pad, width), dtype=local.dtype, device=local.device)
-    send[: local.shape[0]] = local
-    recv = torch.empty((world * pad, width), dtype=local.dtype, device=local.device)
     if world == 1:
-        recv.copy_(send)
+        return local  # one rank owns every block, in order
+    if order is None:
+        order = torch.as_tensor(gather_order(n, world, block), device=local.device)
+    pad = order.numel() // world if world else 0
+    width = local.shape[1]
+    if local.shape[0] == pad:
+        send = local.contiguous()
     else:
-        dist.all_gather_into_tensor(recv, send, group=group)
+        send = torch.zeros((pad, width), dtype=local.dtype, device=local.device)
+        send[: local.shape[0]] = local
+    recv = torch.empty((world * pad, width), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    valid = order >= 0
     out = torch.empty((n, width), dtype=local.dtype, device=local.device)
-    for r in range(world):
-        idx = torch.as_tensor(shard_indices(n, r, world, block), device=local.device)
-        out[idx] = recv[r * pad: r * pad + int(sizes[r])]
+    out.index_copy_(0, order[valid], recv[valid])
     return out
+
+
+def solve_shards_distributed(build_shard: Callable, n: int, *, itol: float = 1e-3, max_steps: int = 100,
+                             gather: bool = True, block: int = BLOCK, group: Any = None,
+                             local_solver: Callable | None = None, order=None):
+    """Solve a batch of ``n`` problems across all ranks, every rank BUILDING ONLY ITS OWN SHARD:
+    ``build_shard(indices) -> (ModelBatch, b, i)`` receives the global indices the rank owns (blocks
+    rank, rank + world, ... of ``block`` problems) and returns their models and boundary values -- from a
+    generator seeded by block, a memory-mapped file, ... -- so no rank ever holds the whole batch.
+    Returns ``(summary, counters, indices)``: the global ``[n, 8]`` records with ``gather=True`` (one
+    all-gather each + one indexed copy), else the rank's own.
+    """
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = shard_indices(n, rank, world, block)
+    sub, b_loc, i_loc = build_shard(mine)
+    if len(sub) != mine.size:
+        raise ValueError("build_shard must return one model per index it was given")
+    if local_solver is None:
+        from ._forward import solve_batch
+
+        sol = solve_batch(sub, b=b_loc, i=i_loc, itol=itol, max_steps=max_steps, throw=False, k_max=0)
+        summary, counters = sol.summary, sol.counters
+    else:
+        summary, counters = local_solver(sub, np.broadcast_to(np.asarray(b_loc, dtype=np.float64), (mine.size,)),
+                                         np.broadcast_to(np.asarray(i_loc, dtype=np.float64), (mine.size,)))
+    if not gather:
+        return summary, counters, mine
+    return (gather_records(summary, n, world, rank, block, group, order),
+            gather_records(counters, n, world, rank, block, group, order), mine)
 
 
 def solve_batch_distributed(models: ModelBatch, *, b: Any, i: Any, itol: float = 1e-3, max_steps: int = 100,
                             gather: bool = True, block: int = BLOCK, group: Any = None,
                             local_solver: Callable | None = None):
-    """Solve a batch across all ranks of the default process group.
-
-    Every rank passes the SAME global batch; rank r solves ``shard_indices(n, r, world)``
-    on its own GPU and, with ``gather=True``, all ranks return the global
-    ``(summary[n, 8], counters[n, 8])`` tensors.  ``local_solver(models, b, i)`` ->
-    (summary, counters) tensors exists so that the CPU tests can exercise the
-    sharding and the collective without a GPU; the default is the CUDA path.
+    """Convenience form of ``solve_shards_distributed`` for a batch every rank already holds: every rank
+    passes the SAME global batch and solves ``shard_indices(n, rank, world)`` of it.  (A 10^7-problem batch is
+    960 MB of parameters per rank this way; build the shards per rank instead when that matters.)
+    ``local_solver(models, b, i)`` -> (summary, counters) tensors exists so that the CPU tests can exercise
+    the sharding and the collective without a GPU; the default is the CUDA path.
     """
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = len(models)
-    mine = shard_indices(n, rank, world, block)
     b_all = np.broadcast_to(np.asarray(b, dtype=np.float64), (n,))
     i_all = np.broadcast_to(np.asarray(i, dtype=np.float64), (n,))
-    sub = models[mine] if mine.size else ModelBatch(np.zeros(0, np.int32), np.zeros((0, _lib.NPARAM)))
-    if local_solver is None:
-        from ._forward import solve_batch
+    empty = ModelBatch(np.zeros(0, np.int32), np.zeros((0, _lib.NPARAM)))
 
-        sol = solve_batch(sub, b=b_all[mine], i=i_all[mine], itol=itol, max_steps=max_steps, throw=False, k_max=0)
-        summary, counters = sol.summary, sol.counters
-    else:
-        summary, counters = local_solver(sub, b_all[mine], i_all[mine])
-    if not gather:
-        return summary, counters, mine
-    return (gather_records(summary, n, world, rank, block, group),
-            gather_records(counters, n, world, rank, block, group), mine)
+    def build(idx):
+        return (models[idx] if idx.size else empty), b_all[idx], i_all[idx]
+
+    return solve_shards_distributed(build, n, itol=itol, max_steps=max_steps, gather=gather, block=block,
+                                    group=group, local_solver=local_solver)
 
 
 def profile_slice(batch: int, rank: int, world: int) -> slice:

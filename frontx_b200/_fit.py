@@ -187,6 +187,28 @@ def _scaled_fit(batch, o: np.ndarray, theta: Any, sigma: Any, *, mode: int, D0=N
     return d0_t, cost, status
 
 
+def generation_cost(D: Any, X: Any, o: Any, theta: Any, sigma: Any = 1, *, i: float, b: float,  # noqa: N803, PLR0913
+                    fit_D0: str | None = "data", k_max: int = 512, S_data: float | None = None) -> np.ndarray:  # noqa: N803
+    """``cost(candidate(x))`` of the reference's ``fit`` (fit.py:125-151) for a whole population at once:
+    ``X[n_params, S]`` holds S candidate parameter vectors of the model family ``D``; returns their S costs.
+    One ``fx_solve_batch`` launch (dense output) + one ``fx_scaled_fit_batch`` launch."""
+    torch = _lib.require_cuda()
+    o_a = np.ascontiguousarray(o, dtype=np.float64).reshape(-1)
+    X = np.asarray(X, dtype=np.float64).reshape(len(get_params(D)), -1)
+    cand = _candidates(D, X)
+    sols = solve_batch(cand, b=b, i=i, throw=False, k_max=k_max)
+    if fit_D0 == "data":
+        _, cost, _ = _scaled_fit(sols, o_a, theta, sigma, mode=1)
+    elif fit_D0 == "sorptivity":
+        d0 = (S_data / sols.sorptivity()) ** 2
+        _, cost, _ = _scaled_fit(sols, o_a, theta, sigma, mode=2, D0=d0)
+    else:
+        _, cost, _ = _scaled_fit(sols, o_a, theta, sigma, mode=0)
+    trunc = sols.counters[:, _lib.C_KNOTS] > sols.k_max
+    cost = torch.where(trunc, torch.full_like(cost, float("inf")), cost)
+    return cost.cpu().numpy()
+
+
 def fit(D: Any, o: Any, theta: Any, /, sigma: Any = 1, *, i: float, b: float,  # noqa: N803, PLR0913
         fit_D0: str | None = "data", max_steps: int = 15, k_max: int = 512, seed: Any = None,  # noqa: N803
         popsize: int = 15, polish: bool = True):
@@ -212,22 +234,9 @@ def fit(D: Any, o: Any, theta: Any, /, sigma: Any = 1, *, i: float, b: float,  #
         raise ValueError("differential evolution needs min and max on every Param")
     o_a = np.ascontiguousarray(o, dtype=np.float64).reshape(-1)
     S_data = float(data_sorptivity(o_a, theta, b=b, i=i)) if fit_D0 == "sorptivity" else None
-    torch = _lib.require_cuda()
 
     def generation(X: np.ndarray) -> np.ndarray:
-        X = np.asarray(X, dtype=np.float64).reshape(len(params), -1)
-        cand = _candidates(D, X)
-        sols = solve_batch(cand, b=b, i=i, throw=False, k_max=k_max)
-        if fit_D0 == "data":
-            _, cost, _ = _scaled_fit(sols, o_a, theta, sigma, mode=1)
-        elif fit_D0 == "sorptivity":
-            d0 = (S_data / sols.sorptivity()) ** 2
-            _, cost, _ = _scaled_fit(sols, o_a, theta, sigma, mode=2, D0=d0)
-        else:
-            _, cost, _ = _scaled_fit(sols, o_a, theta, sigma, mode=0)
-        trunc = sols.counters[:, _lib.C_KNOTS] > sols.k_max
-        cost = torch.where(trunc, torch.full_like(cost, float("inf")), cost)
-        return cost.cpu().numpy()
+        return generation_cost(D, X, o_a, theta, sigma, i=i, b=b, fit_D0=fit_D0, k_max=k_max, S_data=S_data)
 
     bounds = [(p.min, p.max) for p in params]
     x0 = np.array([p.value for p in params])
@@ -247,4 +256,4 @@ def fit(D: Any, o: Any, theta: Any, /, sigma: Any = 1, *, i: float, b: float,  #
     return out
 
 
-__all__ = ("Param", "ScaledSolution", "fit", "get_params", "set_param_values")
+__all__ = ("Param", "ScaledSolution", "fit", "generation_cost", "get_params", "set_param_values")

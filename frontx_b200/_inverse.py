@@ -2,11 +2,18 @@
 batched ``inverse`` entry point.
 
 Reference: src/frontx/_inverse/interpolated.py:18-73 (PCHIP of theta(o); PCHIP of
-o(theta) on sorted theta; ``D = -(do/dtheta * Int_i^theta o dtheta)/2``) and
-src/frontx/_inverse/sorptivity.py:8-19.  The PCHIP slopes, the per-interval cubic
-integrals and their running sum are one scan kernel (``fx_inverse_batch``);
-queries at arbitrary theta are ``fx_inverse_query_batch``.  theta must be
-strictly monotone in o (the reference's ``jnp.unique`` sort is then a reversal).
+o(theta) on ``jnp.unique``-sorted theta; ``D = -(do/dtheta * Int_i^theta o dtheta)/2``)
+and src/frontx/_inverse/sorptivity.py:8-19.  The PCHIP slopes, the per-interval cubic
+integrals and their running sum are one scan kernel (``fx_inverse_batch``); queries at
+arbitrary theta are ``fx_inverse_query_batch``; value, derivative and antiderivative
+of the forward interpolant are ``fx_pchip_query_batch`` on what the same scan leaves
+behind when o and theta swap roles.
+
+A profile whose theta is strictly monotone in o -- the case the scan is built for -- needs
+no sort: ``jnp.unique`` is then a reversal.  Anything else (plateaus at theta = i, repeated
+or noisy values, an appended ``i`` equal to the last value) goes through
+``fx_unique_batch``: a stable radix sort by theta and a first-occurrence dedupe, exactly
+what ``jnp.unique(theta, return_index=True)`` returns (interpolated.py:44-45).
 """
 
 from __future__ import annotations
@@ -19,6 +26,28 @@ from . import _lib
 from ._boltzmann import AbstractSolution, boltzmannmethod
 
 
+def _stream(torch, dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def unique_profile(o: Any, theta: Any, *, device: Any = None):
+    """``theta, idx = jnp.unique(theta, return_index=True); o = o[idx]`` for ONE profile, on the GPU.
+    Returns (o_u, theta_u, idx) device tensors of the deduplicated length, theta ascending."""
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    o_t = torch.as_tensor(o, dtype=torch.float64, device=dev).reshape(-1).contiguous()
+    th_t = torch.as_tensor(theta, dtype=torch.float64, device=dev).reshape(-1).contiguous()
+    n = int(o_t.numel())
+    o_u, th_u = torch.empty_like(o_t), torch.empty_like(th_t)
+    idx = torch.empty((n,), dtype=torch.int32, device=dev)
+    count = torch.zeros((1,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().fx_unique_batch(1, n, o_t.data_ptr(), th_t.data_ptr(), o_u.data_ptr(), th_u.data_ptr(),
+                                              idx.data_ptr(), count.data_ptr(), _stream(torch, dev)))
+    m = int(count.item())
+    return o_u[:m], th_u[:m], idx[:m]
+
+
 class BatchInverse:
     """Result of ``inverse(o, theta)`` for [batch, npts] profiles; tensors stay on the GPU."""
 
@@ -28,6 +57,9 @@ class BatchInverse:
         self._sorp = sorp
         self.status = status
         self._slope, self._anti = slope, anti
+        # profiles that needed the unique-sort: their own scan of the sorted, deduplicated rows + the theta
+        # the integral starts from (the caller's last value, interpolated.py:40,50)
+        self._deduped: dict[int, tuple["BatchInverse", float]] = {}
 
     def D(self, theta_query: Any):
         """InterpolatedSolution.D at theta_query[batch, q] (NaN outside each profile's range)."""
@@ -45,8 +77,9 @@ class BatchInverse:
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().fx_inverse_query_batch(batch, npts, self.o.data_ptr(), self.theta.data_ptr(),
                                                          self._slope.data_ptr(), self._anti.data_ptr(), q,
-                                                         tq.data_ptr(), out.data_ptr(),
-                                                         torch.cuda.current_stream(dev).cuda_stream))
+                                                         tq.data_ptr(), out.data_ptr(), _stream(torch, dev)))
+        for p, (sub, i_ref) in self._deduped.items():
+            out[p] = _deduped_D(sub, i_ref, tq[p:p + 1])[0]
         return out
 
     def _need_sorp(self):
@@ -72,24 +105,30 @@ class BatchInverse:
         return self._sorp[:, 1] + 0.5 * (th0 + b_) * o0 - i_ * oi
 
 
-def inverse(o: Any, theta: Any, *, device: Any = None, throw: bool = True, sorptivity: bool = True,
-            query: bool = True) -> BatchInverse:
-    """``InterpolatedSolution(o, theta).D`` for a batch of profiles, on the GPU.
-
-    ``o`` and ``theta`` are [batch, npts] (or [npts]); numpy arrays or CUDA tensors.
-    ``sorptivity=False`` skips the sorptivity integrals of the forward interpolant (a second PCHIP
-    slope per point: a quarter of the kernel's time), ``query=False`` the two knot arrays that
-    ``BatchInverse.D(theta_query)`` needs (16 B/point more written): D at the knots only.
-    """
+def _deduped_D(sub: BatchInverse, i_ref: float, tq):
+    """D(theta) of a profile that went through the unique-sort.  Its rows are in ascending theta, so the scan
+    measured Int o dtheta from the LARGEST theta; the reference measures it from theta = i
+    (``c = Iodtheta(i)``, interpolated.py:50,65):  D = -(o'(theta) (I(theta) - I(i)))/2 = D_scan + o'(theta) I(i)/2."""
     torch = _lib.require_cuda()
-    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-    o_t = torch.as_tensor(o, dtype=torch.float64, device=dev)
-    th_t = torch.as_tensor(theta, dtype=torch.float64, device=dev)
-    if o_t.ndim == 1:
-        o_t, th_t = o_t.unsqueeze(0), th_t.unsqueeze(0)
-    if o_t.shape != th_t.shape or o_t.ndim != 2:
-        raise ValueError("o and theta must have the same [batch, npts] shape")
-    o_t, th_t = o_t.contiguous(), th_t.contiguous()
+    dev = sub.o.device
+    npts, q = int(sub.o.shape[1]), int(tq.shape[1])
+    tq = tq.contiguous()
+    at_i = torch.full((1, 1), float(i_ref), dtype=torch.float64, device=dev)
+    ant_i = torch.empty((1, 1), dtype=torch.float64, device=dev)
+    der = torch.empty((1, q), dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    args = (1, npts, sub.theta.data_ptr(), sub.o.data_ptr(), sub._slope.data_ptr(), sub._anti.data_ptr())
+    with torch.cuda.device(dev):  # the inverse interpolant o(theta): x = theta, y = o, extrapolate=False
+        _lib.check(L.fx_pchip_query_batch(*args, 1, at_i.data_ptr(), 1, 0, None, None, ant_i.data_ptr(),
+                                          _stream(torch, dev)))
+        _lib.check(L.fx_pchip_query_batch(*args, q, tq.data_ptr(), 1, 0, None, der.data_ptr(), None,
+                                          _stream(torch, dev)))
+    return BatchInverse.D(sub, tq) + der * ant_i[0, 0] / 2
+
+
+def _scan(o_t, th_t, sorptivity: bool, query: bool):
+    torch = _lib.require_cuda()
+    dev = o_t.device
     batch, npts = o_t.shape
     D = torch.empty_like(o_t)
     slope = torch.empty_like(o_t) if query else None
@@ -100,20 +139,92 @@ def inverse(o: Any, theta: Any, *, device: Any = None, throw: bool = True, sorpt
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().fx_inverse_batch(batch, npts, o_t.data_ptr(), th_t.data_ptr(), D.data_ptr(),
                                                ptr(sorp), status.data_ptr(), ptr(slope), ptr(anti),
-                                               torch.cuda.current_stream(dev).cuda_stream))
-    res = BatchInverse(o_t, th_t, D, sorp, status, slope, anti)
-    if throw and int(status.sum().item()) != 0:
-        raise ValueError("theta must be strictly monotone in o for every profile")
+                                               _stream(torch, dev)))
+    return BatchInverse(o_t, th_t, D, sorp, status, slope, anti)
+
+
+def inverse(o: Any, theta: Any, *, device: Any = None, throw: bool = True, sorptivity: bool = True,
+            query: bool = True, unique: bool = True) -> BatchInverse:
+    """``InterpolatedSolution(o, theta).D`` for a batch of profiles, on the GPU.
+
+    ``o`` and ``theta`` are [batch, npts] (or [npts]); numpy arrays or CUDA tensors.
+    ``sorptivity=False`` skips the sorptivity integrals of the forward interpolant (a second PCHIP
+    slope per point: a quarter of the kernel's time), ``query=False`` the two knot arrays that
+    ``BatchInverse.D(theta_query)`` needs (16 B/point more written): D at the knots only.
+
+    Profiles whose theta is strictly monotone in o take the single-pass scan as they are.  With
+    ``unique=True`` (default, the reference's behaviour) every other profile is sorted by theta and
+    deduplicated on the device first (``jnp.unique``, interpolated.py:44-45) and its D evaluated at the
+    caller's points; ``unique=False`` leaves such profiles flagged (``status`` 1).  ``throw`` raises if a
+    profile is left without a valid inverse (fewer than two distinct theta values).
+    """
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    o_t = torch.as_tensor(o, dtype=torch.float64, device=dev)
+    th_t = torch.as_tensor(theta, dtype=torch.float64, device=dev)
+    if o_t.ndim == 1:
+        o_t, th_t = o_t.unsqueeze(0), th_t.unsqueeze(0)
+    if o_t.shape != th_t.shape or o_t.ndim != 2:
+        raise ValueError("o and theta must have the same [batch, npts] shape")
+    o_t, th_t = o_t.contiguous(), th_t.contiguous()
+    res = _scan(o_t, th_t, sorptivity, query)
+    flagged = torch.nonzero(res.status != 0).reshape(-1).tolist() if unique else []
+    for p in flagged:
+        o_u, th_u, _ = unique_profile(o_t[p], th_t[p], device=dev)
+        if o_u.numel() < 2:
+            continue  # a constant profile has no inverse: stays flagged
+        sub = _scan(o_u.unsqueeze(0).contiguous(), th_u.unsqueeze(0).contiguous(), False, True)
+        if int(sub.status[0].item()) != 0:
+            continue
+        res._deduped[p] = (sub, float(th_t[p, -1].item()))
+        res.D_at_knots[p] = _deduped_D(sub, res._deduped[p][1], th_t[p:p + 1])[0]  # at the caller's points
+        res.status[p] = 0
+    if throw and int(res.status.sum().item()) != 0:
+        raise ValueError("theta must take at least two distinct values in every profile" if unique else
+                         "theta must be strictly monotone in o for every profile (unique=False)")
     return res
+
+
+class _ForwardInterpolant:
+    """PCHIP theta(o) of one profile: knot slopes and knot antiderivative values from the scan kernel run
+    with the roles of o and theta swapped; value / derivative / antiderivative by fx_pchip_query_batch."""
+
+    def __init__(self, o: np.ndarray, theta: np.ndarray) -> None:
+        torch = _lib.require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.x = torch.as_tensor(o, dtype=torch.float64, device=dev).reshape(1, -1).contiguous()
+        self.y = torch.as_tensor(theta, dtype=torch.float64, device=dev).reshape(1, -1).contiguous()
+        swapped = _scan(self.y, self.x, False, True)  # the kernel's "theta" argument is the abscissa
+        if int(swapped.status[0].item()) != 0:
+            raise ValueError("o must be strictly increasing")
+        self.slope, self.anti = swapped._slope, swapped._anti
+
+    def query(self, o: Any, which: int) -> np.ndarray:
+        """which = 0 value, 1 derivative, 2 antiderivative; the end cubics extrapolate (scipy/interpax default)."""
+        torch = _lib.require_cuda()
+        dev = self.x.device
+        oo = np.asarray(o, dtype=np.float64)
+        xq = torch.as_tensor(np.ascontiguousarray(oo.reshape(-1)), device=dev)
+        q = int(xq.numel())
+        out = torch.empty((1, q), dtype=torch.float64, device=dev)
+        ptrs = [None, None, None]
+        ptrs[which] = out.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().fx_pchip_query_batch(1, int(self.x.shape[1]), self.x.data_ptr(), self.y.data_ptr(),
+                                                       self.slope.data_ptr(), self.anti.data_ptr(), q, xq.data_ptr(),
+                                                       0, 1, ptrs[0], ptrs[1], ptrs[2], _stream(torch, dev)))
+        res = out[0].cpu().numpy().reshape(oo.shape)
+        return float(res) if oo.ndim == 0 else res
 
 
 class InterpolatedSolution(AbstractSolution):
     """``frontx.InterpolatedSolution`` (src/frontx/_inverse/interpolated.py:11-73).
 
-    ``sol(o)`` interpolates the data with PCHIP, ``sol.D(theta)`` is the diffusivity
-    the profile implies, ``sol.sorptivity()`` its sorptivity.  ``b`` / ``i`` add the
-    boundary point (0, b) and the far-field point (o[-1]+1, i) to the inverse
-    interpolant as the reference does (:32-40).
+    ``sol(o)`` interpolates the data with PCHIP, ``sol.d_do(o)`` is that interpolant's derivative
+    (_boltzmann.py:130-135), ``sol.D(theta)`` the diffusivity the profile implies, ``sol.sorptivity(o)``
+    its sorptivity.  ``b`` / ``i`` add the boundary point (0, b) and the far-field point (o[-1]+1, i) to
+    the inverse interpolant as the reference does (:32-40); repeated theta values are collapsed onto their
+    first occurrence (:44-45).
     """
 
     def __init__(self, o: Any, theta: Any, /, *, b: float | None = None, i: float | None = None) -> None:
@@ -121,7 +232,7 @@ class InterpolatedSolution(AbstractSolution):
         theta = np.asarray(theta, dtype=np.float64)
         if o.ndim != 1 or o.shape != theta.shape:
             raise ValueError("o and theta must be 1-D arrays of the same length")
-        self._fwd = inverse(o, theta)  # forward interpolant data + sorptivity integrals
+        self._fwd = _ForwardInterpolant(o, theta)  # interpolated.py:30
         o_inv, th_inv = o, theta
         if b is not None:
             o_inv = np.insert(o_inv, 0, 0.0)
@@ -129,74 +240,40 @@ class InterpolatedSolution(AbstractSolution):
         if i is not None:
             o_inv = np.append(o_inv, o_inv[-1] + 1)
             th_inv = np.append(th_inv, i)
-        self.oi = float(o_inv[-1])
-        self._inv = self._fwd if (b is None and i is None) else inverse(o_inv, th_inv)
+        self.oi = float(o_inv[-1])  # :42
+        # jnp.unique + PchipInterpolator(theta, o, extrapolate=False), its derivative and antiderivative, and
+        # c = Iodtheta(i) with i the last value of the (extended) data (:40,44-50)
+        self._inv = inverse(o_inv, th_inv, sorptivity=False)
         self._o, self._theta = o, theta
 
     @boltzmannmethod
     def __call__(self, o: Any) -> Any:  # interpolated.py:52-57: the forward PCHIP theta(o)
-        torch = _lib.require_cuda()
-        oo = np.asarray(o, dtype=np.float64)
-        f = self._fwd
-        # theta(o) = value of the forward PCHIP: evaluate it as the inverse of (theta, o) swapped
-        fwd = _forward_interpolant(f)
-        out = fwd(torch.as_tensor(oo.reshape(1, -1), device=f.o.device))[0].cpu().numpy().reshape(oo.shape)
-        return float(out) if oo.ndim == 0 else out
+        return self._fwd.query(o, 0)
 
     @boltzmannmethod
-    def d_do(self, o: Any) -> Any:
-        raise NotImplementedError("InterpolatedSolution.d_do is not part of the accelerated path")
+    def d_do(self, o: Any) -> Any:  # _boltzmann.py:130-135: jax.grad of __call__ = the PCHIP's derivative
+        return self._fwd.query(o, 1)
 
-    def D(self, theta: Any, /) -> Any:  # interpolated.py:59-67
+    def D(self, theta: Any, /) -> Any:  # noqa: N802  interpolated.py:59-67
         torch = _lib.require_cuda()
         th = np.asarray(theta, dtype=np.float64)
-        out = self._inv.D(torch.as_tensor(th.reshape(1, -1), device=self._inv.o.device))[0]
-        out = out.cpu().numpy().reshape(th.shape)
+        tq = torch.as_tensor(np.ascontiguousarray(th.reshape(1, -1)), device=self._inv.o.device)
+        out = self._inv.D(tq)[0].cpu().numpy().reshape(th.shape)
         return float(out) if th.ndim == 0 else out
 
     @property
     def i(self) -> float:
-        return float(self._theta[-1]) if self.oi == self._o[-1] else float(self(self.oi))
+        return float(self(self.oi))
 
     def sorptivity(self, o: Any = 0) -> Any:  # interpolated.py:69-73
-        if np.ndim(o) != 0 or float(o) != 0.0:
-            raise NotImplementedError("InterpolatedSolution.sorptivity is accelerated for o=0 only")
-        f = self._fwd
-        raw = float((f._sorp[0, 0] + f._sorp[0, 2]).item())  # Int_0^{o_last} theta do (PCHIP)
-        o_last = float(self._o[-1])
-        th_oi = self(self.oi)
-        # (I(oi) - I(0)) - i*(oi - 0); beyond the data the forward PCHIP extrapolates (scipy default)
-        extra = 0.0
-        if self.oi != o_last:
-            raise NotImplementedError("sorptivity with an appended far-field point is not accelerated")
-        return (raw + extra) - th_oi * (self.oi - 0.0)
-
-
-def _forward_interpolant(f: BatchInverse):
-    """theta(o) of the forward PCHIP, through the query kernel on the swapped data.
-
-    The query kernel evaluates a PCHIP's derivative and antiderivative; the VALUE of
-    the forward interpolant is recovered here from its antiderivative's derivative,
-    i.e. by a dedicated value kernel -- see fx_pchip_eval_batch.
-    """
-    torch = _lib.require_cuda()
-
-    def run(oq):
-        oq = oq.contiguous()
-        batch, npts = f.o.shape
-        q = int(oq.shape[1])
-        out = torch.empty((batch, q), dtype=torch.float64, device=oq.device)
-        with torch.cuda.device(oq.device):
-            _lib.check(_lib.lib().fx_pchip_eval_batch(batch, npts, f.o.data_ptr(), f.theta.data_ptr(), q,
-                                                      oq.data_ptr(), out.data_ptr(),
-                                                      torch.cuda.current_stream(oq.device).cuda_stream))
-        return out
-
-    return run
+        A = self._fwd.query  # noqa: N806  antiderivative of the forward PCHIP, end cubics extrapolated
+        oo = np.asarray(o, dtype=np.float64)
+        out = (A(self.oi, 2) - A(oo, 2)) - self.i * (self.oi - oo)
+        return float(out) if oo.ndim == 0 else out
 
 
 def sorptivity(o: Any, theta: Any, /, *, b: float, i: float) -> float:
     """``frontx.sorptivity`` (src/frontx/_inverse/sorptivity.py:8-19): trapezoid of theta - i
     over o with the boundary point (0, b) prepended; the sum runs on the GPU."""
-    res = inverse(np.asarray(o, dtype=np.float64), np.asarray(theta, dtype=np.float64), throw=False)
+    res = inverse(np.asarray(o, dtype=np.float64), np.asarray(theta, dtype=np.float64), throw=False, unique=False)
     return float(res.sorptivity_trapezoid(b, i)[0].item())

@@ -55,6 +55,8 @@ EXPORTS = (
     "fx_inverse_batch",
     "fx_inverse_query_batch",
     "fx_pchip_eval_batch",
+    "fx_pchip_query_batch",
+    "fx_unique_batch",
     "fx_measure_fp64_peak",
     "fx_set_kernel_timing",
     "fx_last_solve_kernel_ms",
@@ -88,6 +90,8 @@ def lib() -> C.CDLL:
     L.fx_inverse_batch.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
     L.fx_inverse_query_batch.argtypes = [i64, i64, vp, vp, vp, vp, i64, vp, vp, vp]
     L.fx_pchip_eval_batch.argtypes = [i64, i64, vp, vp, i64, vp, vp, vp]
+    L.fx_pchip_query_batch.argtypes = [i64, i64, vp, vp, vp, vp, i64, vp, i32, i32, vp, vp, vp, vp]
+    L.fx_unique_batch.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, vp]
     L.fx_measure_fp64_peak.argtypes = [C.POINTER(dbl), vp]
     L.fx_set_kernel_timing.argtypes = [i32]
     L.fx_set_kernel_timing.restype = None
@@ -96,7 +100,8 @@ def lib() -> C.CDLL:
     L.fx_launch_count.restype = i64
     L.fx_last_error.restype = C.c_char_p
     for name in ("fx_solve_batch", "fx_solve_batch_host", "fx_solve_flowrate_batch", "fx_eval_batch", "fx_scaled_fit_batch", "fx_diffusivity_batch",
-                 "fx_inverse_batch", "fx_inverse_query_batch", "fx_pchip_eval_batch", "fx_measure_fp64_peak",
+                 "fx_inverse_batch", "fx_inverse_query_batch", "fx_pchip_eval_batch", "fx_pchip_query_batch",
+                 "fx_unique_batch", "fx_measure_fp64_peak",
                  "fx_version",
                  "fx_device_count"):
         getattr(L, name).restype = C.c_int

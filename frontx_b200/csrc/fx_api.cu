@@ -4,6 +4,9 @@
 // and diffusivity kernels, and a DFMA micro-benchmark for the FP64 roofline.
 #include <cuda_runtime.h>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -375,9 +378,12 @@ __global__ void scaled_fit_kernel(long long n, const int* __restrict__ counters,
       double lam = 1e-3;
       sums(exp(u), c, g, h);
       st = 1;  // max_steps_reached unless the loop converges
-      for (int it = 0; it < 100; it++) {
+      for (int it = 0; it < 200; it++) {
         if (!(h > 0.0)) { st = (g == 0.0) ? 0 : 2; break; }  // flat: nothing to fit / no direction
-        const double du = -g / (h * (1.0 + lam));
+        // trust region: D0 changes by at most e^1.5 per step.  Far from the minimum only a few data points
+        // see the front, h is tiny and the raw Gauss-Newton step can jump to D0 = inf (where the curve is the
+        // constant b and the cost happens to be lower than at a poor start)
+        const double du = fmax(-1.5, fmin(1.5, -g / (h * (1.0 + lam))));
         double c2, g2, h2;
         sums(exp(u + du), c2, g2, h2);
         if (c2 <= c) {
@@ -390,6 +396,22 @@ __global__ void scaled_fit_kernel(long long n, const int* __restrict__ counters,
           lam *= 10.0;
           if (lam > 1e12) { st = 0; break; }  // cannot decrease any further: at the minimum to rounding
         }
+      }
+      // Polish: the minimiser is the root of g(u) = sum r dr/du, which the sums give analytically; a few secant
+      // steps from the last Gauss-Newton iterate pin it to rounding (the damped iteration stops once the COST
+      // no longer decreases, which leaves u good to ~1e-8 only).
+      if (st == 0 && h > 0.0) {
+        double u0 = u, g0 = g, u1 = u - g / h, c1, g1, h1;
+        sums(exp(u1), c1, g1, h1);
+        for (int it = 0; it < 12 && g1 != g0 && g1 != 0.0; it++) {
+          const double u2 = u1 - g1 * (u1 - u0) / (g1 - g0);
+          if (!(fabs(u2 - u) < 1e-4)) break;  // stay at the minimum the iteration found
+          u0 = u1; g0 = g1;
+          u1 = u2;
+          sums(exp(u1), c1, g1, h1);
+          if (fabs(u1 - u0) <= 4e-16 * fmax(1.0, fabs(u1))) break;
+        }
+        if (fabs(g1) <= fabs(g) && fabs(u1 - u) < 1e-4) { u = u1; c = c1; }
       }
       D0 = exp(u);
     } else {
@@ -845,6 +867,72 @@ int fx_pchip_eval_batch(int64_t batch, int64_t npts, const double* x, const doub
       batch, npts, x, y, q, x_query, y_out);
   g_launches++;
   FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int fx_pchip_query_batch(int64_t batch, int64_t npts, const double* x, const double* y, const double* slope,
+                         const double* anti, int64_t q, const double* x_query, int32_t per_profile,
+                         int32_t extrapolate, double* value, double* derivative, double* antiderivative,
+                         void* stream) {
+  if (batch < 0 || npts < 2 || q < 0) return fail(FX_ERR_ARG, "bad sizes%s");
+  if (batch == 0 || q == 0) return FX_OK;
+  if (!x || !y || !slope || !x_query) return fail(FX_ERR_ARG, "null pointer argument%s");
+  if (antiderivative && !anti) return fail(FX_ERR_ARG, "the antiderivative needs the knot antiderivative values%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  fx::pchip_query_kernel<<<grid_for(batch * q, 256, di.sms), 256, 0, (cudaStream_t)stream>>>(
+      batch, npts, x, y, slope, anti, q, x_query, per_profile, extrapolate, value, derivative, antiderivative);
+  g_launches++;
+  FX_CUDA(cudaGetLastError());
+  return FX_OK;
+}
+
+int fx_unique_batch(int64_t batch, int64_t npts, const double* o, const double* theta, double* o_out,
+                    double* theta_out, int32_t* index_out, int64_t* n_unique, void* stream) {
+  if (batch < 0 || npts < 1) return fail(FX_ERR_ARG, "bad sizes%s");
+  if (batch == 0) return FX_OK;
+  if (npts > 2147483647LL) return fail(FX_ERR_ARG, "a profile exceeds 2^31-1 points%s");
+  if (!o || !theta || !o_out || !theta_out || !n_unique) return fail(FX_ERR_ARG, "null pointer argument%s");
+  DeviceInfo di;
+  int rc = device_info(&di);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = (int)npts;
+  // stable LSD radix sort of (key(theta), index): equal thetas keep the caller's order, so the first of
+  // every run is the first occurrence, which is what jnp.unique(return_index=True) returns
+  size_t tmp_sort = 0, tmp_sel = 0;
+  FX_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const unsigned long long*)nullptr,
+                                          (unsigned long long*)nullptr, (const int*)nullptr, (int*)nullptr, n, 0, 64, s));
+  FX_CUDA(cub::DeviceSelect::UniqueByKey(nullptr, tmp_sel, (const unsigned long long*)nullptr, (const int*)nullptr,
+                                         (unsigned long long*)nullptr, (int*)nullptr, (int*)nullptr, n, s));
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t kb = up((size_t)n * sizeof(unsigned long long)), ib = up((size_t)n * sizeof(int));
+  const size_t tb = up(tmp_sort > tmp_sel ? tmp_sort : tmp_sel);
+  Scratch scr(s);
+  FX_CUDA(cudaMallocAsync(&scr.p, 3 * kb + 3 * ib + tb + 256, s));
+  char* base = static_cast<char*>(scr.p);
+  unsigned long long* key0 = reinterpret_cast<unsigned long long*>(base);
+  unsigned long long* key1 = reinterpret_cast<unsigned long long*>(base + kb);
+  unsigned long long* key2 = reinterpret_cast<unsigned long long*>(base + 2 * kb);
+  int* idx0 = reinterpret_cast<int*>(base + 3 * kb);
+  int* idx1 = reinterpret_cast<int*>(base + 3 * kb + ib);
+  int* idx2 = reinterpret_cast<int*>(base + 3 * kb + 2 * ib);
+  void* tmp = base + 3 * kb + 3 * ib;
+  int* count = reinterpret_cast<int*>(base + 3 * kb + 3 * ib + tb);
+  const int g = grid_for(npts, 256, di.sms);
+  for (int64_t p = 0; p < batch; p++) {
+    const double* th = theta + p * npts;
+    fx::unique_keys_kernel<<<g, 256, 0, s>>>(npts, th, key0, idx0);
+    size_t t1 = tmp_sort, t2 = tmp_sel;
+    FX_CUDA(cub::DeviceRadixSort::SortPairs(tmp, t1, key0, key1, idx0, idx1, n, 0, 64, s));
+    FX_CUDA(cub::DeviceSelect::UniqueByKey(tmp, t2, key1, idx1, key2, idx2, count, n, s));
+    fx::unique_gather_kernel<<<g, 256, 0, s>>>(count, idx2, o + p * npts, th, o_out + p * npts, theta_out + p * npts,
+                                              index_out ? index_out + p * npts : nullptr,
+                                              reinterpret_cast<long long*>(n_unique) + p);
+    g_launches += 2;  // ours; the sort and the selection are CUB's
+    FX_CUDA(cudaGetLastError());
+  }
   return FX_OK;
 }
 

@@ -75,7 +75,15 @@ constexpr int INV_GROUP = 32; // tiles per look-back group (one warp reads a gro
 #ifndef FX_INV_DEFER
 #define FX_INV_DEFER 2
 #endif
+// 1: a tile finds its direction (theta rising or falling along the traversal) from its own points and
+// publishes it as +1 / -1 (0: not monotone); the profile is monotone iff the signs of all its tiles add up
+// to +-(number of tiles that hold an interval).  0: every tile loads the profile's last two values from
+// global memory to learn the direction (two dependent L2 round trips per tile).
+#ifndef FX_INV_TILESIGN
+#define FX_INV_TILESIGN 1
+#endif
 constexpr int INV_DEFER = FX_INV_DEFER;  // a tile's output is written this many tiles later
+static_assert(INV_DEFER >= 1 && INV_DEFER <= 2, "the kernel loop's exit test looks at the first and last deferred tile only");
 
 __device__ __forceinline__ double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 
@@ -140,6 +148,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // trip when the value is there instead of three (flag, fence, data), no fence on the reader's
 // side (each 8-byte access is atomic): the look-back sits on every tile's critical path.
 __device__ __forceinline__ bool is_unset(double v) { return __double_as_longlong(v) == -1LL; }
+// ... so nothing published may BE that pattern: a quiet NaN keeps its payload through additions, and a
+// profile that holds the all-ones NaN (a buffer preset to 0xff, a missing-data marker) would otherwise
+// publish totals that read as "not there yet" and leave every later tile of the profile spinning.
+__device__ __forceinline__ double published(double v) {
+  return is_unset(v) ? __longlong_as_double(0x7ff8000000000000LL) : v;
+}
 // A value that is not there yet is polled at a short fixed pause.  The waits sit on the kernel's
 // critical chain (publish -> group total -> look-back -> next publish): pauses of 128 ns and more,
 // or a growing pause, were measured two to three times slower.
@@ -257,7 +271,7 @@ template <bool EDGE, bool SORP>
 __device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, const double* __restrict__ o_g,
                                               long long n, long long rb, const double (&x)[INV_NP],
                                               const double (&y)[INV_NP], double (&d)[INV_ITEMS + 1],
-                                              double (&I)[INV_ITEMS], double& sumF, double& sumT, bool up,
+                                              double (&I)[INV_ITEMS], double& sumF, double& sumT, bool& up,
                                               bool& mono) {
   // One pass along the thread's points, each step using what the one before left behind: the interval
   // after point j (its steps and a number with the sign of its secant -- steps of 1e-77 would have to
@@ -323,6 +337,9 @@ __device__ __forceinline__ void compute_chunk(const double* __restrict__ th_g, c
       bool exists = true;
       if (EDGE) exists = rb + j - 1 <= n - 2;
       v = exists ? v : 0.0;
+#if FX_INV_TILESIGN
+      if (j == 1) up = hc > 0.0;  // the thread's own direction: its first interval (the tile compares the threads')
+#endif
       if (exists) mono = mono && (up ? hc > 0.0 : hc < 0.0);
       if (SORP) {
         const double trap = gc * (0.5 * (x[j] + x[j + 1]));
@@ -373,6 +390,7 @@ __device__ __forceinline__ double pchip_extrapolated_head(const double* o_g, con
 // everything behind its own next ticket waits with it.)
 struct InvArgs {
   long long batch, npts, ntiles;  // tiles of INV_WPTS points per profile
+  double inv_ntiles;              // 1 / ntiles: a ticket is split into (profile, tile) without a 64-bit division
   const double* o;
   const double* theta;
   double* D;
@@ -474,10 +492,25 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
     return tk;
   };
   long long p = 0, t = 0;
+#ifndef FX_INV_FASTDIV
+#define FX_INV_FASTDIV 1
+#endif
   auto decode_ticket = [&](unsigned long long raw) {
     const long long tk = (long long)__shfl_sync(0xffffffffu, raw, 0);
+#if FX_INV_FASTDIV
+    // tk / ntiles by a double-precision reciprocal and one correction step (exact: tickets stay far below
+    // 2^52); the 64-bit integer division is a ~70-instruction subroutine, once per tile and thread
+    long long pq = (long long)((double)tk * A.inv_ntiles);
+    long long tr = tk - pq * A.ntiles;
+    if (tr < 0) { pq--; tr += A.ntiles; }
+    if (tr >= A.ntiles) { pq++; tr -= A.ntiles; }
+    const bool live = tk < total_tiles;
+    p = live ? pq : A.batch;
+    t = live ? tr : tk - A.batch * A.ntiles;
+#else
     p = tk < total_tiles ? tk / A.ntiles : A.batch;
     t = tk - p * A.ntiles;
+#endif
   };
   decode_ticket(take_ticket());
   bool have = p < A.batch;
@@ -486,8 +519,10 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
     const long long wbase = n - t * INV_WPTS - INV_WPTS;
     const double* th_g = A.theta + p * n;
     const double* o_g = A.o + p * n;
+#if !FX_INV_TILESIGN
     dir_a = th_g[n - 2];
     dir_b = th_g[n - 1];
+#endif
     if (bulk_tile(t)) {
       request_warp<false, A16>(th_g, n, wbase, s_in[0][wid], lane);
       request_warp<false, A16>(o_g, n, wbase, s_in[1][wid], lane);
@@ -521,10 +556,21 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
       collect_chunk(s_in[1][wid], lane, y);
       double I[INV_ITEMS], sumF, sumT;
       bool mono;
-      const bool up = dir_step > 0.0, flat = !(dir_step != 0.0);
+      bool up = dir_step > 0.0;
       if (bulk_tile(t)) compute_chunk<false, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
       else compute_chunk<true, SORP>(th_g, o_g, n, rb, x, y, d, I, sumF, sumT, up, mono);
-      const bool anybad = __any_sync(0xffffffffu, flat || !mono);
+#if FX_INV_TILESIGN
+      // +1: every interval of the tile rises along the traversal, -1: every one falls, 0: neither
+      // (threads beyond the profile's end hold no interval and do not vote)
+      const bool has = rb <= n - 2;
+      const unsigned hasm = __ballot_sync(0xffffffffu, has);
+      const unsigned upm = __ballot_sync(0xffffffffu, has && up);
+      const bool allmono = __all_sync(0xffffffffu, !has || mono);
+      const double tile_sign = (allmono && hasm) ? (upm == hasm ? 1.0 : (upm == 0u ? -1.0 : 0.0)) : 0.0;
+#else
+      const bool anybad = __any_sync(0xffffffffu, !(dir_step != 0.0) || !mono);
+      const double tile_sign = anybad ? 1.0 : 0.0;
+#endif
 
       double run = 0.0;
 #pragma unroll
@@ -545,10 +591,10 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
       // ---- publish; the last tile of a group (supergroup) closes it ---------------------------------
       if (lane == 0) {
         double* ag = A.agg + (p * A.ntiles + t) * INV_NAGG;
-        __stcg(ag + 0, carry);
-        __stcg(ag + 1, f);
-        __stcg(ag + 2, z);
-        __stcg(ag + 3, anybad ? 1.0 : 0.0);
+        __stcg(ag + 0, published(carry));
+        __stcg(ag + 1, published(f));
+        __stcg(ag + 2, published(z));
+        __stcg(ag + 3, tile_sign);
       }
       // whoever arrives last in a full group closes it (nobody ever waits for a particular tile here);
       // the count comes back while the next tile is being requested
@@ -574,7 +620,7 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
       if (lane == 0) {
         double* gt = A.gtot + (this_p * A.ngroups + G) * INV_NAGG;
 #pragma unroll
-        for (int c = 0; c < INV_NAGG; c++) __stcg(gt + c, tot[c]);
+        for (int c = 0; c < INV_NAGG; c++) __stcg(gt + c, published(tot[c]));
         if (G / INV_GROUP < A.nsuper) arrived2 = atomicAdd(A.scount + this_p * A.nsuper + G / INV_GROUP, 1);
       }
       arrived2 = __shfl_sync(0xffffffffu, arrived2, 0);
@@ -586,7 +632,7 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
         if (lane == 0) {
           double* st = A.stot + (this_p * A.nsuper + S) * INV_NAGG;
 #pragma unroll
-          for (int c = 0; c < INV_NAGG; c++) __stcg(st + c, tot[c]);
+          for (int c = 0; c < INV_NAGG; c++) __stcg(st + c, published(tot[c]));
         }
       }
     }
@@ -645,8 +691,14 @@ __global__ void __launch_bounds__(INV_BLOCK, FX_INV_CTAS) inverse_scan_kernel(co
         const double* th_g = A.theta + p2 * n;
         const double* o_g = A.o + p2 * n;
         const double* own = A.agg + (p2 * A.ntiles + t2) * INV_NAGG;
-        const double nbad = tot[3] + __ldcg(own + 3);
-        A.status[p2] = (nbad != 0.0) ? 1 : 0;
+        const double ssum = tot[3] + __ldcg(own + 3);
+#if FX_INV_TILESIGN
+        // the last tile holds no interval when it holds a single point
+        const double voters = (double)(A.ntiles - (((n - 1) % INV_WPTS) == 0 ? 1 : 0));
+        A.status[p2] = (fabs(ssum) == voters) ? 0 : 1;
+#else
+        A.status[p2] = (ssum != 0.0) ? 1 : 0;
+#endif
         if (SORP) {
           double F = tot[1] + __ldcg(own + 1), Z = tot[2] + __ldcg(own + 2);
           double* out = A.sorp + p2 * 4;
@@ -721,6 +773,77 @@ __global__ void inverse_query_kernel(long long batch, long long n, const double*
   }
 }
 
+// Value, derivative and antiderivative of the PCHIP y(x) of a profile at arbitrary x, from the knot slopes
+// and knot antiderivative values the scan kernel leaves behind (x strictly monotone, either direction;
+// anti[k] = Int from the caller's LAST point to knot k).  extrapolate != 0: the end cubics continue beyond
+// the data (scipy/interpax PchipInterpolator and PPoly default); else NaN there.  One thread per query.
+__global__ void pchip_query_kernel(long long batch, long long n, const double* __restrict__ x,
+                                   const double* __restrict__ y, const double* __restrict__ slope,
+                                   const double* __restrict__ anti, long long q, const double* __restrict__ xq,
+                                   int per_profile, int extrapolate, double* __restrict__ val,
+                                   double* __restrict__ der, double* __restrict__ ant) {
+  const double nan = __longlong_as_double(0x7ff8000000000000LL);
+  long long total = batch * q;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+       g += (long long)gridDim.x * blockDim.x) {
+    long long p = g / q;
+    const double* xs = x + p * n;
+    const double* ys = y + p * n;
+    const double* dd = slope + p * n;
+    const double* aa = anti ? anti + p * n : nullptr;
+    const double v = xq[per_profile ? g : g - p * q];
+    const bool decreasing = xs[0] > xs[n - 1];
+    const double xmin = decreasing ? xs[n - 1] : xs[0], xmax = decreasing ? xs[0] : xs[n - 1];
+    double rv = nan, rd = nan, ra = nan;
+    if (v == v && (extrapolate || (v >= xmin && v <= xmax))) {
+      long long lo = 0, hi = n;  // searchsorted(x_ascending, v, side='right') - 1, clipped to [0, n-2]
+      while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (xs[decreasing ? n - 1 - mid : mid] <= v) lo = mid + 1; else hi = mid;
+      }
+      long long k = lo - 1;
+      if (k < 0) k = 0;
+      if (k > n - 2) k = n - 2;
+      const long long j0 = decreasing ? n - 1 - k : k, j1 = decreasing ? j0 - 1 : j0 + 1;
+      const double x0 = xs[j0], x1 = xs[j1], y0 = ys[j0], y1 = ys[j1], d0 = dd[j0], d1 = dd[j1];
+      const double h = x1 - x0, m = (y1 - y0) / h;
+      const double t = (d0 + d1 - 2.0 * m) / h;
+      const double c0 = t / h, c1 = (m - d0) / h - t;
+      const double u = v - x0;
+      rv = ((c0 * u + c1) * u + d0) * u + y0;
+      rd = (3.0 * c0 * u + 2.0 * c1) * u + d0;
+      if (aa) ra = aa[j0] + (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + d0 * 0.5) * u + y0) * u;
+    }
+    if (val) val[g] = rv;
+    if (der) der[g] = rd;
+    if (ant) ant[g] = ra;
+  }
+}
+
+// ---- jnp.unique(theta, return_index=True) (src/frontx/_inverse/interpolated.py:44-45) ----------------
+// order-preserving 64-bit key of a double: -0.0 is +0.0, negatives below positives, NaN last
+__global__ void unique_keys_kernel(long long n, const double* __restrict__ v, unsigned long long* __restrict__ key,
+                                   int* __restrict__ idx) {
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n; g += (long long)gridDim.x * blockDim.x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v[g] + 0.0);
+    key[g] = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    idx[g] = (int)g;
+  }
+}
+__global__ void unique_gather_kernel(const int* __restrict__ count, const int* __restrict__ idx,
+                                     const double* __restrict__ a, const double* __restrict__ b,
+                                     double* __restrict__ a_out, double* __restrict__ b_out, int* __restrict__ idx_out,
+                                     long long* __restrict__ n_out) {
+  const long long m = *count;
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < m; g += (long long)gridDim.x * blockDim.x) {
+    const int j = idx[g];
+    a_out[g] = a[j];
+    b_out[g] = b[j];
+    if (idx_out) idx_out[g] = j;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_out = m;
+}
+
 // slope of the PCHIP y(x) at knot j, read straight from global memory (x ascending or descending)
 __device__ __forceinline__ double pchip_slope_global(const double* __restrict__ x,
                                                      const double* __restrict__ y, long long j, long long n) {
@@ -774,6 +897,7 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   a.batch = batch;
   a.npts = npts;
   a.ntiles = (npts + INV_WPTS - 1) / INV_WPTS;
+  a.inv_ntiles = 1.0 / (double)a.ntiles;
   a.o = o;
   a.theta = theta;
   a.D = D;
@@ -796,6 +920,11 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   a.gcount = reinterpret_cast<int*>(scratch + agg_bytes);
   a.scount = a.gcount + (size_t)batch * (size_t)a.ngroups;
   a.ticket = reinterpret_cast<unsigned long long*>(scratch + agg_bytes + cnt_bytes);
+  struct Guard {  // the scratch goes back to the pool, in stream order, on every way out
+    char* p;
+    cudaStream_t s;
+    ~Guard() { cudaFreeAsync(p, s); }
+  } guard{scratch, s};
   e = cudaMemsetAsync(scratch, 0xff, agg_bytes, s);  // the "unset" pattern (see is_unset)
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(scratch + agg_bytes, 0, cnt_bytes + 64, s);
@@ -819,9 +948,7 @@ inline cudaError_t inverse_launch(long long batch, long long npts, const double*
   if (grid < 1) grid = 1;
   kern<<<grid, INV_BLOCK, dyn, s>>>(a);
   *launches = 1;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  return cudaFreeAsync(scratch, s);
+  return cudaGetLastError();
 }
 
 }  // namespace fx

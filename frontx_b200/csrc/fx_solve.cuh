@@ -66,12 +66,6 @@ namespace fx {
 #ifndef FX_SPEC_MAX_DEPTH
 #define FX_SPEC_MAX_DEPTH 5  // up to 2^depth - 1 speculative shots per problem and round
 #endif
-#ifndef FX_LATE_NBIS
-#define FX_LATE_NBIS 0       // > 0: a bisection that has taken this many steps without converging is
-#endif                       // probably one of the ~0.5 % that never will: speculate at once, FX_LATE_DEPTH
-#ifndef FX_LATE_DEPTH        // levels per round, while the bulk of the batch still fills the lanes
-#define FX_LATE_DEPTH 4
-#endif
 #ifndef FX_TAIL_DENSE
 #define FX_TAIL_DENSE 0      // 1: in the end phase only as many CTA layers as the outstanding shots can fill
 #endif                       // take work (full warps, few warps per scheduler), the rest drain and sleep
@@ -210,7 +204,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
   // registers, not arithmetic, bound the resident warps of this kernel.
   __shared__ double s_dpar[NDP][SOLVE_BLOCK];  // the model's derived constants
   __shared__ double s_cold[FLOW ? 6 : 5][SOLVE_BLOCK];  // b, i, direction, bisection value of the shot, t1, (q)
-  __shared__ int s_cnt[3][SOLVE_BLOCK];        // attempts, rejections, knots of the shot
+  __shared__ int s_cnt[4][SOLVE_BLOCK];        // attempts, rejections, knots of the shot; RHS count at the last attempt's end
   __shared__ BlockCtx ctx;                     // bucket geometry (same for every thread)
 
   const int tid = threadIdx.x;
@@ -274,6 +268,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
   int& att_shot = s_cnt[0][tid];
   int& rej_shot = s_cnt[1][tid];
   int& n_knots = s_cnt[2][tid];
+  int& rhs_mark = s_cnt[3][tid];
 
   for (;;) {
     // ---- fetch: pop shots for the lanes that have none -------------------------------------
@@ -405,7 +400,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
               t0 = A.ob;
               y00 = bnd_b;
               y01 = d_shot;
-              att_shot = rej_shot = rhs_shot = 0;
+              att_shot = rej_shot = rhs_shot = rhs_mark = 0;
               te = t0;
               ye0 = y00;
               ye1 = y01;
@@ -447,7 +442,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       t0 = A.ob;
       y00 = bnd_b;
       y01 = -s_cold[FLOW ? 5 : 0][tid] * iD;
-      att_shot = rej_shot = rhs_shot = 0;
+      att_shot = rej_shot = rhs_shot = rhs_mark = 0;
       te = t0;
       ye0 = y00;
       ye1 = y01;
@@ -468,7 +463,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       t0 = A.ob;
       y00 = bnd_b;
       y01 = d_shot;
-      att_shot = rej_shot = rhs_shot = 0;
+      att_shot = rej_shot = rhs_shot = rhs_mark = 0;
       te = t0;
       ye0 = y00;
       ye1 = y01;
@@ -491,6 +486,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       mode = M_INIT1;
     } else if (mode == M_INIT1) {
       rhs_shot++;
+      rhs_mark = rhs_shot;  // the attempts' right-hand sides are counted from here
       double dt = init_dt(y00, y01, fs(0, 0), fs(0, 1), R.F0, R.F1, h, dsz, tol, mt);
       t1 = t0 + dt;
       h = t1 - t0;
@@ -543,6 +539,20 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     if (att_end) {
       att_shot++;
       StepEnd s = step_finish(tab, att_ok, fs, y00, y01, yp0, yp1, f0, f1, h, tol, mt);
+      // A FROZEN integrator: if this attempt leaves (t0, y0, f(t0, y0), h) bit for bit as it found them, the next
+      // attempt -- a pure function of that state -- repeats it exactly, and so does every one after it, until
+      // max_ode_steps ends the shot without an event.  That is how a too-steep shot dies against a sharp front:
+      // the step size underflows (t0 + dt == t0, h = 0) within a few hundred attempts and the remaining
+      // ~3700 of diffrax's 4096 are copies, each "accepted".  They are counted, not integrated: same
+      // residual, same counters, same knots (the CPU twin runs them all; the tests demand bit equality).
+      bool frozen;
+      {
+        const double nt0 = s.keep ? t1 : t0;
+        const bool same_f = !s.keep || (f0 == fsm[0][tid][0] && f1 == fsm[0][tid][1]);
+        frozen = (nt0 == t0) && (s.y10 == y00) && (s.y11 == y01) && same_f && (((nt0 + s.dt_next) - nt0) == h);
+      }
+      const int rhs_att = rhs_shot - rhs_mark;  // right-hand sides of this attempt
+      rhs_mark = rhs_shot;
       if (s.keep) {
         t0 = t1;
         y00 = s.y10;
@@ -560,6 +570,21 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
         }
       } else {
         rej_shot++;
+      }
+      if (frozen && !shot_end && att_shot < A.max_ode_steps) {
+        const int left = A.max_ode_steps - att_shot;  // the copies
+        att_shot += left;
+        rhs_shot += left * rhs_att;
+        if (s.keep) {
+          if (A.knots && node <= 0) {
+            double* knot_row = A.knots + (size_t)prob * A.k_max * FX_KNOT;
+            for (int k = n_knots; k < A.k_max && k < n_knots + left; k++)
+              *reinterpret_cast<double4*>(knot_row + (size_t)k * FX_KNOT) = make_double4(t0, y00, y01, f1);
+          }
+          n_knots += left;
+        } else {
+          rej_shot += left;
+        }
       }
       if (!shot_end) {
         if (att_shot >= A.max_ode_steps) {
@@ -691,10 +716,15 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
               const unsigned u = (((unsigned)prob * 2654435761u) ^ ((unsigned)n_shots * 40503u)) >> 24;
               if ((rho - lo) * 256 > (hi - lo) * (long long)u) d++;
             }
-#if FX_LATE_NBIS > 0
-            if (bis.n_bis >= FX_LATE_NBIS && d < (FX_LATE_DEPTH < SPEC_MAX_DEPTH ? FX_LATE_DEPTH : SPEC_MAX_DEPTH))
-              d = FX_LATE_DEPTH < SPEC_MAX_DEPTH ? FX_LATE_DEPTH : SPEC_MAX_DEPTH;
-#endif
+            // Ring entries pushed and not yet popped must never exceed its capacity (the bucket's problems
+            // + one spare entry per resident lane).  Batches sized to fill the lanes stay far below it; as
+            // insurance no batch is pushed into a ring that is already half full.
+            if (d > 1) {
+              const unsigned long long tl = *(volatile unsigned long long*)&ctx.ctl->tail;
+              unsigned long long hd = *(volatile unsigned long long*)&ctx.ctl->head;
+              if (hd < (unsigned long long)ctx.n_work) hd = (unsigned long long)ctx.n_work;
+              if (tl > hd && (long long)(tl - hd) > ctx.ring_cap / 2) d = 1;
+            }
             if (d > 1 && bs.y == 0) {
               unsigned int sl = atomicAdd(A.spec_next, 1u);
               if (sl < A.spec_slots) bs.y = (int)sl + 1; else d = 1;

@@ -195,6 +195,29 @@ int fx_inverse_query_batch(int64_t batch, int64_t npts, const double *o, const d
 int fx_pchip_eval_batch(int64_t batch, int64_t npts, const double *x, const double *y, int64_t q,
                         const double *x_query, double *y_out, void *stream);
 
+/* Value, derivative and antiderivative of a profile's PCHIP y(x) at arbitrary x, from the knot slopes
+ * and knot antiderivative values fx_inverse_batch leaves behind (its do_dtheta / Iodtheta outputs; call
+ * it with the roles of o and theta swapped to get those of the FORWARD interpolant theta(o)).  Replaces
+ * InterpolatedSolution.d_do (src/frontx/_boltzmann.py:130-135 = the derivative of the forward PCHIP) and
+ * the PPoly antiderivative behind InterpolatedSolution.sorptivity(o) (interpolated.py:69-73).
+ *   x strictly monotone (either direction); anti[k] = Int from the LAST point to knot k, may be NULL
+ *   x_query [batch][q] (per_profile=1) or [q]; value / derivative / antiderivative [batch][q], any NULL
+ *   extrapolate != 0: the end cubics continue beyond the data (PchipInterpolator/PPoly default), else NaN.
+ * All pointers device. */
+int fx_pchip_query_batch(int64_t batch, int64_t npts, const double *x, const double *y, const double *slope,
+                         const double *anti, int64_t q, const double *x_query, int32_t per_profile,
+                         int32_t extrapolate, double *value, double *derivative, double *antiderivative,
+                         void *stream);
+
+/* jnp.unique(theta, return_index=True); o = o[indices] (interpolated.py:44-45) per profile: theta sorted
+ * ascending, equal values collapsed onto their FIRST occurrence (-0.0 == +0.0, NaN last).  The compacted
+ * rows are written to the front of o_out / theta_out [batch][npts] (and the original indices to index_out,
+ * may be NULL); n_unique[batch] receives their lengths.  The sort is CUB's stable radix sort on an
+ * order-preserving key; a profile that is already strictly monotone needs none of this (fx_inverse_batch
+ * takes it in either direction).  All pointers device. */
+int fx_unique_batch(int64_t batch, int64_t npts, const double *o, const double *theta, double *o_out,
+                    double *theta_out, int32_t *index_out, int64_t *n_unique, void *stream);
+
 /* measured FP64 FMA throughput of the current device, FLOP/s (roofline denominator) */
 int fx_measure_fp64_peak(double *flops_per_s, void *stream);
 

@@ -55,7 +55,22 @@ def build(force: bool = False) -> Path:
     return LIB
 
 
+def use_native() -> str:
+    """For the CPU TIMING arm of bench.py: rebuild both checkers with -O3 -march=native ON THIS BOX (into
+    oracle/_native/, git-ignored, never shipped: the instruction set is the box's own) and load those instead
+    of the portable builds.  Same sources, -ffp-contract=off: same results, only faster.  Returns the flags."""
+    global _lib, _twin, LIB, _TWIN_PATH
+    proc = subprocess.run(["make", "-C", str(HERE), "-B", "native"], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("building the native oracle failed:\n" + proc.stdout + proc.stderr)
+    LIB = HERE / "_native" / "libfx_oracle.so"
+    _TWIN_PATH = HERE / "_native" / "libfx_twin.so"
+    _lib = _twin = None
+    return "-O3 -march=native -ffp-contract=off"
+
+
 _twin = None
+_TWIN_PATH = None
 
 
 def twin() -> C.CDLL:
@@ -68,7 +83,7 @@ def twin() -> C.CDLL:
             has_fma = " fma " in open("/proc/cpuinfo").read().replace("\n", " ")
         except OSError:
             pass
-        L = C.CDLL(str(HERE / ("libfx_twin_fma.so" if has_fma else "libfx_twin.so")))
+        L = C.CDLL(str(_TWIN_PATH or HERE / ("libfx_twin_fma.so" if has_fma else "libfx_twin.so")))
         dp = C.POINTER(C.c_double)
         ip = C.POINTER(C.c_int32)
         L.fxt_D.argtypes = [C.c_int, dp, C.c_double, dp]
@@ -161,6 +176,7 @@ def lib() -> C.CDLL:
         L.fxo_inverse.argtypes = [C.c_int64, dp, dp, dp, dp, dp]
         L.fxo_inverse.restype = C.c_int
         L.fxo_num_threads.restype = C.c_int
+        L.fxo_diag_get.argtypes = [C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 

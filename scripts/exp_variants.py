@@ -15,17 +15,15 @@ OUT = ROOT / "build_variants"
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC", "-shared"]
 VARIANTS = {
-    "base": [],
-    "d7": ["-DFX_SPEC_MAX_DEPTH=7"],
-    "d7_dense": ["-DFX_SPEC_MAX_DEPTH=7", "-DFX_TAIL_DENSE=1"],
-    "d6_dense": ["-DFX_SPEC_MAX_DEPTH=6", "-DFX_TAIL_DENSE=1"],
-    "d5_dense": ["-DFX_TAIL_DENSE=1"],
+    "base": ["-DFX_LATE_NBIS=0"],
     "late18_5": ["-DFX_LATE_NBIS=18", "-DFX_LATE_DEPTH=5"],
-    "late18_5_d7_dense": ["-DFX_LATE_NBIS=18", "-DFX_LATE_DEPTH=5", "-DFX_SPEC_MAX_DEPTH=7", "-DFX_TAIL_DENSE=1"],
-    "late17_4_d7_dense": ["-DFX_LATE_NBIS=17", "-DFX_LATE_DEPTH=4", "-DFX_SPEC_MAX_DEPTH=7", "-DFX_TAIL_DENSE=1"],
-    "late19_5_d7_dense": ["-DFX_LATE_NBIS=19", "-DFX_LATE_DEPTH=5", "-DFX_SPEC_MAX_DEPTH=7", "-DFX_TAIL_DENSE=1"],
-    "late16_3_d7_dense": ["-DFX_LATE_NBIS=16", "-DFX_LATE_DEPTH=3", "-DFX_SPEC_MAX_DEPTH=7", "-DFX_TAIL_DENSE=1"],
-    "b96x7": ["-DFX_SOLVE_BLOCK=96", "-DFX_SOLVE_CTAS=7"],
+    "late16_3": ["-DFX_LATE_NBIS=16", "-DFX_LATE_DEPTH=3"],
+    "late16_4": ["-DFX_LATE_NBIS=16", "-DFX_LATE_DEPTH=4"],
+    "late17_4": ["-DFX_LATE_NBIS=17", "-DFX_LATE_DEPTH=4"],
+    "late17_5": ["-DFX_LATE_NBIS=17", "-DFX_LATE_DEPTH=5"],
+    "late19_5": ["-DFX_LATE_NBIS=19", "-DFX_LATE_DEPTH=5"],
+    "late20_5": ["-DFX_LATE_NBIS=20", "-DFX_LATE_DEPTH=5"],
+    "late18_4": ["-DFX_LATE_NBIS=18", "-DFX_LATE_DEPTH=4"],
 }
 
 

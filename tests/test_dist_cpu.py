@@ -141,3 +141,69 @@ def test_two_rank_inverse_matches_single_process(tmp_path, fxo):
         np.testing.assert_array_equal(np.load(tmp_path / f"invD{r}.npy"), ref_D)
         np.testing.assert_array_equal(np.load(tmp_path / f"invS{r}.npy"), ref_S)
     assert np.load(tmp_path / "invM0.npy").tolist() == [0, 3] and np.load(tmp_path / "invM1.npy").tolist() == [3, 5]
+
+
+def test_c3_rows_are_block_seeded():
+    """bench.c3_rows: any rank can build any shard of config C3 without the rest of the batch."""
+    import bench
+
+    full = bench.c3_rows(np.arange(3 * bench.C3_BLOCK + 77))
+    idx = np.concatenate([np.arange(5, 40), np.arange(bench.C3_BLOCK - 3, bench.C3_BLOCK + 9), np.arange(2 * bench.C3_BLOCK, 2 * bench.C3_BLOCK + 4)])
+    part = bench.c3_rows(idx)
+    np.testing.assert_array_equal(part.params, full.params[idx])
+    np.testing.assert_array_equal(part.model_id, full.model_id[idx])
+    assert (full.model_id[0::2] == bench.BROOKS_COREY).all() and (full.model_id[1::2] == bench.LETD).all()
+    p = full.params
+    bc, ld = p[0::2], p[1::2]
+    assert bc[:, 0].min() >= 0.2 and bc[:, 0].max() <= 0.6 and bc[:, 2].min() >= 1e-6 and bc[:, 2].max() <= 1e-5
+    assert ld[:, 1].min() >= 1e3 and ld[:, 1].max() <= 2e4 and ld[:, 2].min() >= 1.0 and ld[:, 2].max() <= 1.6
+
+
+def _shards_worker(rank: int, world: int, port: int, n: int, out_dir: str) -> None:
+    import torch
+    import torch.distributed as dist
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+    from oracle import fxo
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    built = []
+
+    def build(idx):  # the rank builds ONLY its own rows
+        built.append(idx.copy())
+        return bench.c3_rows(idx), bench.B_BOUNDARY, bench.I_INITIAL
+
+    def oracle_solver(sub, b, i):
+        r = fxo.solve_batch(sub.model_id, sub.params, b, i, nthreads=1)
+        return torch.from_numpy(r["summary"]), torch.from_numpy(r["counters"])
+
+    summary, counters, mine = _dist.solve_shards_distributed(build, n, block=4, local_solver=oracle_solver)
+    assert len(built) == 1 and np.array_equal(built[0], mine)
+    np.save(os.path.join(out_dir, f"ssum{rank}.npy"), summary.numpy())
+    np.save(os.path.join(out_dir, f"scnt{rank}.npy"), counters.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shards_built_per_rank(tmp_path, fxo):
+    """C3 through solve_shards_distributed at world_size 2: every rank builds only its block-cyclic shard, one
+    all-gather + one indexed copy give every rank the global records in the caller's order."""
+    import torch.multiprocessing as mp
+
+    import bench
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    n, world = 22, 2
+    mp.spawn(_shards_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+    models = bench.c3_rows(np.arange(n))
+    ref = fxo.solve_batch(models.model_id, models.params, bench.B_BOUNDARY, bench.I_INITIAL)
+    for r in range(world):
+        np.testing.assert_array_equal(np.load(tmp_path / f"ssum{r}.npy"), ref["summary"])
+        np.testing.assert_array_equal(np.load(tmp_path / f"scnt{r}.npy"), ref["counters"])
+    order = _dist.gather_order(n, world, 4)
+    assert sorted(order[order >= 0].tolist()) == list(range(n)) and (order >= 0).sum() == n

@@ -339,7 +339,8 @@ def test_model_mask_hint():
     np.testing.assert_array_equal(full.summary.cpu().numpy(), hinted.summary.cpu().numpy())
     partial = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False, options={"model_mask": 1 << _lib.LETD})
     c = partial.counters.cpu().numpy()
-    assert (c[mb.model_id == _lib.BROOKS_COREY, 0] == -1).all() and (c[mb.model_id == _lib.LETD, 0] == 0).all()
+    assert (c[mb.model_id == _lib.BROOKS_COREY, 0] == -1).all()
+    np.testing.assert_array_equal(c[mb.model_id == _lib.LETD], full.counters.cpu().numpy()[mb.model_id == _lib.LETD])
     np.testing.assert_array_equal(partial.summary.cpu().numpy()[mb.model_id == _lib.LETD],
                                   full.summary.cpu().numpy()[mb.model_id == _lib.LETD])
 
@@ -532,10 +533,13 @@ def inverse_profiles():
     yield "two", np.array([0.0, 2.0]), np.array([1.0, 0.25])
     o5 = np.linspace(0, 20 / 1.3, 20_000)
     yield "C5-like 20k", o5, np.exp(-1.3 * o5)
+    for n in (255, 256, 257, 258, 513):  # around the 256-point warp tile
+        yield f"tile boundary {n}", np.linspace(0, 5, n), np.exp(-np.linspace(0, 5, n))
     yield "tile boundary 1024", np.linspace(0, 5, 1024), np.exp(-np.linspace(0, 5, 1024))
     yield "tile boundary 1025", np.linspace(0, 5, 1025), np.exp(-np.linspace(0, 5, 1025))
     yield "tile boundary 2049", np.linspace(0, 5, 2049), np.exp(-np.linspace(0, 5, 2049))
-    # more than 32 tiles of 1024 points: the two-level look-back (group totals) comes into play
+    # more than 32 warp tiles of 256 points (8 192 points): group totals come into play; supergroup totals
+    # (262 144 points) and the loop over more than 32 of them are in test_inverse_supergroup_paths_vs_oracle
     o6 = np.linspace(0, 20 / 0.9, 100_000)
     yield "three full groups 100k", o6, np.exp(-0.9 * o6)
     o7 = np.linspace(0, 14, 70_001)
@@ -694,20 +698,145 @@ def test_inverse_long_increasing_and_non_monotone_in_the_bulk(fxo):
         bad = np.exp(-np.linspace(0, 5, 9000))
         bad[where] = bad[where - 1]
         both = np.stack([np.exp(-np.linspace(0, 5, 9000)), bad])
-        st = fx.inverse(np.stack([np.linspace(0, 5, 9000)] * 2), both, throw=False).status.cpu().numpy()
+        st = fx.inverse(np.stack([np.linspace(0, 5, 9000)] * 2), both, throw=False, unique=False).status.cpu().numpy()
         assert st.tolist() == [0, 1]
         up = bad[::-1].copy()  # the same flaw in an increasing profile
-        st = fx.inverse(np.linspace(0, 5, 9000), up, throw=False).status.cpu().numpy()
+        st = fx.inverse(np.linspace(0, 5, 9000), up, throw=False, unique=False).status.cpu().numpy()
+        assert st.tolist() == [1]
+        wrong_way = np.exp(-np.linspace(0, 5, 9000))
+        wrong_way[where:] = wrong_way[where:][::-1]  # every tile monotone, but not all the same way
+        st = fx.inverse(np.linspace(0, 5, 9000), wrong_way, throw=False, unique=False).status.cpu().numpy()
         assert st.tolist() == [1]
 
 
-def test_inverse_rejects_non_monotone():
+def test_inverse_non_monotone_without_the_unique_sort_is_flagged():
     o = np.linspace(0, 5, 64)
     th = np.exp(-o)
     th[30] = th[29]
     with pytest.raises(ValueError, match="monotone"):
-        fx.inverse(o, th)
-    assert int(fx.inverse(o, th, throw=False).status[0]) == 1
+        fx.inverse(o, th, unique=False)
+    assert int(fx.inverse(o, th, throw=False, unique=False).status[0]) == 1
+    assert int(fx.inverse(o, th).status[0]) == 0  # the default sorts and deduplicates, as the reference does
+
+
+def interpolated_cases():
+    """Profiles a measured data set produces and a strictly monotone scan cannot take as they are."""
+    rng = np.random.default_rng(17)
+    o = np.linspace(0, 10, 300)
+    yield "flat far-field tail", o, np.maximum(np.exp(-o), np.exp(-6.0)), None, None
+    yield "flat tail, i= equal to the last value", o, np.maximum(np.exp(-o), np.exp(-6.0)), None, float(np.exp(-6.0))
+    yield "flat head at b", o, np.minimum(0.9, 1.2 * np.exp(-0.5 * o)), None, None
+    noisy = np.exp(-0.6 * o) + 2e-3 * rng.standard_normal(o.size)
+    yield "noisy, not monotone", o, noisy, None, None
+    yield "noisy with b= and i=", o[1:], noisy[1:], 1.01, 1e-4
+    rounded = np.round(np.exp(-0.6 * o), 3)  # a logger with three decimals: many repeated values
+    yield "quantised", o, rounded, None, None
+    yield "monotone with b= and i=", o[1:], np.exp(-0.6 * o[1:]), 1.0, 1e-3
+    o2 = np.linspace(0, 3, 200)
+    yield "increasing with plateaus", o2, np.round(0.2 + 0.5 * np.tanh(o2), 2), None, None
+
+
+@pytest.mark.parametrize("case", list(interpolated_cases()), ids=lambda c: c[0])
+def test_interpolated_solution_vs_scipy_twin(case):
+    """InterpolatedSolution with repeated / unsorted theta (jnp.unique, interpolated.py:44-45), the b= / i=
+    insertions (:32-40), d_do (= the forward PCHIP's derivative, _boltzmann.py:130-135) and sorptivity(o) at any
+    o (:69-73), against the line-for-line scipy twin of tests/test_oracle_inverse.py, within 1e-9."""
+    from test_oracle_inverse import ScipyInterpolated
+
+    _, o, th, b, i = case
+    want = ScipyInterpolated(o, th, b=b, i=i)
+    sol = fx.InterpolatedSolution(o, th, b=b, i=i)
+    assert sol.oi == pytest.approx(float(want.oi), rel=1e-15)
+    every = np.concatenate([th, [v for v in (b, i) if v is not None]])
+    lo, hi = every.min(), every.max()
+    tq = np.concatenate([np.linspace(lo, hi, 501), th[::7], [lo - 1e-3, hi + 1e-3]])
+    got, ref = sol.D(tq), want.D(tq)
+    assert np.array_equal(np.isnan(got), np.isnan(ref))  # extrapolate=False: NaN outside the data
+    fin = ~np.isnan(ref)
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=1e-9, atol=1e-11 * np.abs(ref[fin]).max())
+    oq = np.concatenate([np.linspace(o[0], o[-1], 333), [o[0] - 0.1, o[-1] + 0.5]])  # the end cubics extrapolate
+    np.testing.assert_allclose(sol(oq), want(oq), rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(sol.d_do(oq), want.d_do(oq), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(sol.sorptivity(oq), want.sorptivity(oq), rtol=1e-9, atol=1e-12)
+    assert sol.sorptivity() == pytest.approx(float(want.sorptivity()), rel=1e-9)
+    assert sol.i == pytest.approx(float(want.i), rel=1e-12)
+    # the Solution algebra on top (_boltzmann.py:137-161) now works for interpolated solutions
+    r, t = 0.5 * o[-1], 4.0
+    assert sol.d_dr(r, t) == pytest.approx(float(want.d_do(r / 2.0)) / 2.0, rel=1e-9)
+    assert sol.flux(r, t) == pytest.approx(-float(want.D(want(r / 2.0))) * float(want.d_do(r / 2.0)) / 2.0, rel=1e-8)
+
+
+def test_unique_profile_is_numpy_unique():
+    rng = np.random.default_rng(5)
+    for n in (2, 3, 1000, 70_001):
+        th = np.round(rng.uniform(-1, 1, n), 2 if n > 100 else 6)
+        th[rng.integers(0, n, max(1, n // 50))] = 0.0
+        th[rng.integers(0, n, max(1, n // 50))] = -0.0
+        o = rng.uniform(0, 5, n)
+        o_u, th_u, idx = fx.unique_profile(o, th)
+        want_th, want_idx = np.unique(th, return_index=True)
+        np.testing.assert_array_equal(idx.cpu().numpy(), want_idx)
+        np.testing.assert_array_equal(th_u.cpu().numpy(), want_th)
+        np.testing.assert_array_equal(o_u.cpu().numpy(), o[want_idx])
+
+
+def test_inverse_batch_with_some_profiles_needing_the_sort(fxo):
+    """A batch where two of five profiles have repeated values: those take the unique-sort, the others the
+    plain scan, and every row of D equals the scipy twin at the caller's own points."""
+    from test_oracle_inverse import ScipyInterpolated
+
+    o = np.linspace(0, 8, 4001)
+    rows = [np.exp(-0.5 * o), np.maximum(np.exp(-0.9 * o), 2e-3), 0.1 + 0.8 * np.exp(-1.3 * o),
+            np.round(np.exp(-0.7 * o), 4), 1.0 / (1.0 + o) ** 2]
+    th = np.stack(rows)
+    res = fx.inverse(np.stack([o] * 5), th)
+    assert res.status.cpu().numpy().tolist() == [0] * 5 and sorted(res._deduped) == [1, 3]
+    for j in range(5):
+        want = ScipyInterpolated(o, th[j])
+        np.testing.assert_allclose(res.D_at_knots[j].cpu().numpy(), want.D(th[j]), rtol=1e-9,
+                                   atol=1e-11 * np.abs(want.D(th[j])).max())
+        assert float(res.sorptivity()[j]) == pytest.approx(float(want.sorptivity()), rel=1e-9)
+
+
+def test_inverse_all_ones_nan_pattern_does_not_hang():
+    """A buffer preset to 0xff bytes is a NaN with an all-ones payload, the very pattern the look-back polls for
+    as "not published yet"; published totals are canonicalised, so the launch ends and flags the profile."""
+    import torch
+
+    npts = 300_000  # several look-back groups
+    bad = torch.full((npts,), -1, dtype=torch.int64, device="cuda").view(torch.float64)
+    o = torch.linspace(0, 10, npts, dtype=torch.float64, device="cuda")
+    good = torch.exp(-o)
+    half = good.clone()
+    half[100_000:100_050] = bad[:50]
+    th = torch.stack([bad, good, half])
+    res = fx.inverse(torch.stack([o, o, o]), th, throw=False, unique=False)
+    torch.cuda.synchronize()
+    assert res.status.cpu().numpy().tolist() == [1, 0, 1]
+
+
+@pytest.mark.parametrize("npts,shift", [(300_001, 0), (300_000, 1), (9_000_001, 0)])
+def test_inverse_supergroup_paths_vs_oracle(fxo, npts, shift):
+    """More than 262 144 points close a supergroup total, more than 8.4e6 run the look-back's loop over more
+    than 32 supergroups: both against the oracle, odd lengths and an unaligned view (8-byte copies) included."""
+    import torch
+
+    a = 0.8
+    o = np.linspace(0, 20 / a, npts)
+    th = np.exp(-a * o)
+    rc, D_c, s_pchip, s_trapz = fxo.inverse(o, th)
+    assert rc == 0
+    ot = torch.zeros(npts + shift, dtype=torch.float64, device="cuda")
+    tt = torch.zeros(npts + shift, dtype=torch.float64, device="cuda")
+    ot[shift:] = torch.as_tensor(o, device="cuda")
+    tt[shift:] = torch.as_tensor(th, device="cuda")
+    res = fx.inverse(ot[shift:], tt[shift:])
+    assert int(res.status[0]) == 0
+    D_g = res.D_at_knots[0].cpu().numpy()
+    sel = th > 1e-300
+    np.testing.assert_allclose(D_g[sel], D_c[sel], rtol=1e-9, atol=1e-12 * np.abs(D_c).max())
+    assert float(res.sorptivity()[0]) == pytest.approx(s_pchip, rel=1e-9)
+    assert float(res._sorp[0, 1]) == pytest.approx(s_trapz, rel=1e-11)
 
 
 def test_launch_counter_moves():

@@ -34,6 +34,48 @@ def scipy_twin(o, theta):
     return D, float(sorp)
 
 
+class ScipyInterpolated:
+    """interpolated.py:18-73 line for line, scipy's PchipInterpolator/PPoly in place of interpax's port of them
+    (b=, i= insertions, jnp.unique, extrapolate=False on the inverse, sorptivity at any o)."""
+
+    def __init__(self, o, theta, b=None, i=None):
+        o = np.asarray(o, dtype=np.float64)
+        theta = np.asarray(theta, dtype=np.float64)
+        self._sol = PchipInterpolator(o, theta)
+        if b is not None:
+            o = np.insert(o, 0, 0)
+            theta = np.insert(theta, 0, b)
+        if i is not None:
+            o = np.append(o, o[-1] + 1)
+            theta = np.append(theta, i)
+        else:
+            i = theta[-1]
+        self.oi = o[-1]
+        theta, indices = np.unique(theta, return_index=True)
+        o = o[indices]
+        inverse = PchipInterpolator(theta, o, extrapolate=False)
+        self._do_dtheta = inverse.derivative()
+        self._Iodtheta = inverse.antiderivative()
+        self._c = self._Iodtheta(i)
+
+    def __call__(self, o):
+        return self._sol(o)
+
+    def d_do(self, o):
+        return self._sol.derivative()(o)
+
+    @property
+    def i(self):
+        return self(self.oi)
+
+    def D(self, theta):  # noqa: N802
+        return -(self._do_dtheta(theta) * (self._Iodtheta(theta) - self._c)) / 2
+
+    def sorptivity(self, o=0):
+        anti = self._sol.antiderivative()
+        return (anti(self.oi) - anti(o)) - self.i * (self.oi - o)
+
+
 def profiles():
     rng = np.random.default_rng(7)
     o = np.linspace(0, 20, 100)
@@ -87,3 +129,19 @@ def test_duplicates_are_dropped_like_unique(fxo):
     assert rc == 0
     flat = np.where(th == th[-1])[0]
     assert np.isfinite(Dk[flat[0]]) and np.all(np.isnan(Dk[flat[1:]]))
+
+
+def test_scipy_interpolated_twin_passes_the_reference_tests():
+    """The literal scipy twin used by the GPU tests of duplicates / insertions / d_do / sorptivity(o) reproduces
+    /root/reference/tests/test_inverse.py:29-39,51-62 and agrees with the simpler twin above."""
+    o = np.linspace(0, 20, 100)
+    sol = ScipyInterpolated(o, np.exp(-o))
+    assert sol(o) == pytest.approx(np.exp(-o))
+    theta = np.linspace(1e-6, 1, 100)
+    assert sol.D(theta) == pytest.approx(0.5 * (1 - np.log(theta)), abs=5e-2)
+    assert sol.sorptivity() == pytest.approx(1, abs=1e-4)
+    D, sorp = scipy_twin(o, np.exp(-o))
+    np.testing.assert_array_equal(sol.D(theta), D(theta))
+    assert float(sol.sorptivity()) == sorp
+    # jax.grad of the PCHIP = its derivative; of exp(-o): -exp(-o)
+    assert sol.d_do(o[5:60]) == pytest.approx(-np.exp(-o[5:60]), rel=2e-2)
