@@ -93,28 +93,25 @@ def c3_rows(idx: np.ndarray):
     ids = np.empty(idx.size, dtype=np.int32)
     par = np.zeros((idx.size, 12))
     blocks = idx // C3_BLOCK
-    for blk in np.unique(blocks):
-        rng = np.random.default_rng([1, int(blk)])
-        u = rng.random((C3_BLOCK, 4))
-        k = np.arange(C3_BLOCK) + blk * C3_BLOCK
-        even = k % 2 == 0
-        p = np.zeros((C3_BLOCK, 12))
+    starts = np.flatnonzero(np.r_[True, blocks[1:] != blocks[:-1]])  # idx ascending: one contiguous run per block
+    for a, z in zip(starts, np.r_[starts[1:], idx.size]):
+        blk = int(blocks[a])
+        u = np.random.default_rng([1, blk]).random((C3_BLOCK, 4))[idx[a:z] - blk * C3_BLOCK]
+        even = idx[a:z] % 2 == 0
+        odd = ~even
+        p = par[a:z]
         # Brooks-Corey {n, l, Ks, alpha, theta_r, theta_s}
         p[even, 0] = 0.2 + 0.4 * u[even, 0]
         p[even, 1] = 1.0 + 4.0 * u[even, 1]
         p[even, 2] = np.exp(np.log(1e-6) + np.log(10.0) * u[even, 2])
         p[even, 3], p[even, 4], p[even, 5] = 1.0, 2.378e-5, 0.7
         # LETd {L, E, T, Dwt, theta_r, theta_s}
-        odd = ~even
         p[odd, 0] = 0.004 + 1.496 * u[odd, 0]
         p[odd, 1] = np.exp(np.log(1e3) + np.log(20.0) * u[odd, 1])
         p[odd, 2] = 1.0 + 0.6 * u[odd, 2]
         p[odd, 3] = np.exp(np.log(1e-4) + np.log(20.0) * u[odd, 3])
         p[odd, 4], p[odd, 5] = 0.0198, 0.7
-        sel = blocks == blk
-        loc = idx[sel] - blk * C3_BLOCK
-        par[sel] = p[loc]
-        ids[sel] = np.where(even[loc], BROOKS_COREY, LETD)
+        ids[a:z] = np.where(even, BROOKS_COREY, LETD)
     return ModelBatch(ids, par)
 
 

@@ -37,6 +37,9 @@ class SolveError(RuntimeError):
 def _as_batch(D: Any) -> ModelBatch:
     if isinstance(D, ModelBatch):
         return D
+    owner = getattr(D, "__self__", None)  # solve(D=sol.D) with sol an InterpolatedSolution (tests/test_inverse.py:42-48)
+    if owner is not None and hasattr(owner, "tabulated_model") and getattr(D, "__name__", "") == "D":
+        D = owner.tabulated_model()
     if isinstance(D, _TaggedModel):
         return ModelBatch.from_models([D])
     if isinstance(D, (list, tuple)):

@@ -261,6 +261,30 @@ class InterpolatedSolution(AbstractSolution):
         out = self._inv.D(tq)[0].cpu().numpy().reshape(th.shape)
         return float(out) if th.ndim == 0 else out
 
+    def tabulated_model(self):
+        """``self.D`` as a model the solve kernels evaluate (``frontx_b200.models.Tabulated``): the knots of the
+        inverse interpolant in ascending theta with its slopes and ``Iodtheta - c``.  ``solve(D=sol.D, ...)`` calls
+        this (the reference passes the bound method itself, tests/test_inverse.py:42-48)."""
+        torch = _lib.require_cuda()
+        from .models import Tabulated
+
+        if 0 in self._inv._deduped:  # rows already ascending; the scan measured the integral from the largest theta
+            sub, i_ref = self._inv._deduped[0]
+            dev = sub.o.device
+            at_i = torch.full((1, 1), float(i_ref), dtype=torch.float64, device=dev)
+            ant_i = torch.empty((1, 1), dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().fx_pchip_query_batch(1, int(sub.o.shape[1]), sub.theta.data_ptr(), sub.o.data_ptr(),
+                                                           sub._slope.data_ptr(), sub._anti.data_ptr(), 1, at_i.data_ptr(),
+                                                           1, 0, None, None, ant_i.data_ptr(), _stream(torch, dev)))
+            rows = [sub.theta[0], sub.o[0], sub._slope[0], sub._anti[0] - ant_i[0, 0]]
+        else:  # strictly monotone data in the caller's order: the integral already starts at the last point, theta = i
+            inv = self._inv
+            rows = [inv.theta[0], inv.o[0], inv._slope[0], inv._anti[0]]
+            if bool(rows[0][0] > rows[0][-1]):
+                rows = [r.flip(0) for r in rows]
+        return Tabulated(torch.stack(rows).contiguous())
+
     @property
     def i(self) -> float:
         return float(self(self.oi))

@@ -13,8 +13,8 @@ NPARAM, NSUM, NCNT, KNOT = 12, 8, 8, 4
 LIB_PATH = Path(__file__).resolve().parent / "libfrontx_b200.so"
 
 # model ids (enum fx_model)
-CONSTANT, POWER_LAW, BROOKS_COREY, VAN_GENUCHTEN, LETXS, LETD, LOG = range(7)
-MODEL_NAMES = ("constant", "power_law", "brooks_and_corey", "van_genuchten", "letxs", "letd", "log")
+CONSTANT, POWER_LAW, BROOKS_COREY, VAN_GENUCHTEN, LETXS, LETD, LOG, TABULATED = range(8)
+MODEL_NAMES = ("constant", "power_law", "brooks_and_corey", "van_genuchten", "letxs", "letd", "log", "tabulated")
 
 # summary / counter columns
 S_D_DOB, S_OI, S_THETA_OI, S_S0, S_D_B, S_RESIDUAL, S_LOWER, S_UPPER = range(8)

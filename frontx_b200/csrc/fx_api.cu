@@ -63,26 +63,28 @@ int device_info(DeviceInfo* out) {
 }
 
 // ---- bucketing of a mixed batch by model -----------------------------------
-// scratch layout (unsigned long long): counts[8] | cursors[8] | speculation-slot allocator
-constexpr int SCR_COUNTS = 0, SCR_CURSORS = 8, SCR_WORDS = 16;
+// scratch layout (unsigned long long): counts[16] | cursors[16] | speculation-slot allocator
+constexpr int NSLOT = FX_NUM_MODELS + 1;  // one bucket per model + one for problems that are not solved
+constexpr int SCR_COUNTS = 0, SCR_CURSORS = 16, SCR_WORDS = 32;
+static_assert(NSLOT <= 16, "scratch layout");
 
 // `mask` = the models the caller says are present (bit m; all seven when it does not know): a problem
-// whose model is outside it, or is no model at all, is parked in slot 7 and flagged, never solved
+// whose model is outside it, or is no model at all, is parked in the last slot and flagged, never solved
 __device__ __forceinline__ int bucket_of(int m, unsigned mask) {
-  return (m < 0 || m >= FX_NUM_MODELS || !((mask >> m) & 1u)) ? 7 : m;
+  return (m < 0 || m >= FX_NUM_MODELS || !((mask >> m) & 1u)) ? FX_NUM_MODELS : m;
 }
 
 __global__ void count_models_kernel(long long n, const int* __restrict__ model_id, unsigned mask,
                                     unsigned long long* scratch) {
-  __shared__ unsigned int local[8];
-  if (threadIdx.x < 8) local[threadIdx.x] = 0;
+  __shared__ unsigned int local[NSLOT];
+  if (threadIdx.x < NSLOT) local[threadIdx.x] = 0;
   __syncthreads();
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
     atomicAdd(&local[bucket_of(model_id[j], mask)], 1u);
   }
   __syncthreads();
-  if (threadIdx.x < 8 && local[threadIdx.x])
+  if (threadIdx.x < NSLOT && local[threadIdx.x])
     atomicAdd(&scratch[SCR_COUNTS + threadIdx.x], (unsigned long long)local[threadIdx.x]);
 }
 
@@ -90,16 +92,16 @@ __global__ void scatter_models_kernel(long long n, const int* __restrict__ model
                                       unsigned long long* scratch, int* __restrict__ perm,
                                       int* __restrict__ counters) {
   // bucket-major placement; order inside a bucket is by warp-aggregated cursor
-  long long base[8];
+  long long base[NSLOT];
   long long acc = 0;
-  for (int k = 0; k < 8; k++) {
+  for (int k = 0; k < NSLOT; k++) {
     base[k] = acc;
     acc += (long long)scratch[SCR_COUNTS + k];
   }
   for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n;
        j += (long long)gridDim.x * blockDim.x) {
     const int m = bucket_of(model_id[j], mask);
-    if (m == 7) counters[j * FX_NCNT + 0] = FX_INVALID_MODEL;  // never solved
+    if (m == FX_NUM_MODELS) counters[j * FX_NCNT + 0] = FX_INVALID_MODEL;  // never solved
     unsigned long long pos = atomicAdd(&scratch[SCR_CURSORS + m], 1ull);
     perm[base[m] + (long long)pos] = (int)j;
   }
@@ -149,6 +151,7 @@ int launch_by_id(int model, const fx::SolveArgs& a, int geom, long long n_upper,
     case FX_LETXS: rc = occupancy_of<FX_LETXS>(geom, &bps); break;
     case FX_LETD: rc = occupancy_of<FX_LETD>(geom, &bps); break;
     case FX_LOG: rc = occupancy_of<FX_LOG>(geom, &bps); break;
+    case FX_TABULATED: rc = occupancy_of<FX_TABULATED>(geom, &bps); break;
     default: return fail(FX_ERR_MODEL, "unknown model id%s");
   }
   if (rc) return rc;
@@ -166,7 +169,8 @@ int launch_by_id(int model, const fx::SolveArgs& a, int geom, long long n_upper,
     case FX_VAN_GENUCHTEN: return launch_model<FX_VAN_GENUCHTEN>(a, geom, grid, s);
     case FX_LETXS: return launch_model<FX_LETXS>(a, geom, grid, s);
     case FX_LETD: return launch_model<FX_LETD>(a, geom, grid, s);
-    default: return launch_model<FX_LOG>(a, geom, grid, s);
+    case FX_LOG: return launch_model<FX_LOG>(a, geom, grid, s);
+    default: return launch_model<FX_TABULATED>(a, geom, grid, s);
   }
 }
 
@@ -176,8 +180,8 @@ int launch_by_id(int model, const fx::SolveArgs& a, int geom, long long n_upper,
 struct Fork {
   int dev = -1;
   cudaStream_t owner = nullptr;
-  cudaStream_t streams[FX_NUM_MODELS] = {};
-  cudaEvent_t begin = nullptr, done[FX_NUM_MODELS] = {};
+  cudaStream_t streams[FX_NUM_MODELS] = {}, reserve[FX_NUM_MODELS] = {};
+  cudaEvent_t begin = nullptr, done[FX_NUM_MODELS] = {}, rdone[FX_NUM_MODELS] = {};
   cudaEvent_t k0[FX_NUM_MODELS] = {}, k1[FX_NUM_MODELS] = {};  // kernel timing (fx_set_kernel_timing)
   bool timed[FX_NUM_MODELS] = {};
   std::mutex mu;
@@ -205,7 +209,9 @@ int get_fork(cudaStream_t owner, Fork** out) {
   f->owner = owner;
   for (int m = 0; m < FX_NUM_MODELS; m++) {
     FX_CUDA(cudaStreamCreateWithFlags(&f->streams[m], cudaStreamNonBlocking));
+    FX_CUDA(cudaStreamCreateWithFlags(&f->reserve[m], cudaStreamNonBlocking));
     FX_CUDA(cudaEventCreateWithFlags(&f->done[m], cudaEventDisableTiming));
+    FX_CUDA(cudaEventCreateWithFlags(&f->rdone[m], cudaEventDisableTiming));
     FX_CUDA(cudaEventCreate(&f->k0[m]));
     FX_CUDA(cudaEventCreate(&f->k1[m]));
   }
@@ -456,6 +462,7 @@ __global__ void diffusivity_kernel(long long n, const int* __restrict__ model_id
       case FX_LETXS: diffusivity_one<FX_LETXS>(p, th, o); break;
       case FX_LETD: diffusivity_one<FX_LETD>(p, th, o); break;
       case FX_LOG: diffusivity_one<FX_LOG>(p, th, o); break;
+      case FX_TABULATED: diffusivity_one<FX_TABULATED>(p, th, o); break;
       default: o[0] = o[1] = o[2] = __longlong_as_double(0x7ff8000000000000LL);
     }
   }
@@ -505,6 +512,7 @@ __global__ void flow_finalize_kernel(long long n, const int* __restrict__ model_
       case FX_LETXS: flow_finalize_one<FX_LETXS>(p, q[j], S); break;
       case FX_LETD: flow_finalize_one<FX_LETD>(p, q[j], S); break;
       case FX_LOG: flow_finalize_one<FX_LOG>(p, q[j], S); break;
+      case FX_TABULATED: flow_finalize_one<FX_TABULATED>(p, q[j], S); break;
       default: break;
     }
   }
@@ -628,7 +636,7 @@ int solve_impl(int64_t n, const int32_t* model_id, const double* params, const d
   long long spec_slots = (long long)di.sms * (16384 / fx::SPEC_NODES) + 8;
   if (spec_slots > n) spec_slots = n;
   const size_t off_ctl = up((SCR_WORDS + 8) * sizeof(unsigned long long));
-  const size_t off_bstate = off_ctl + up(8 * sizeof(fx::QueueCtl));
+  const size_t off_bstate = off_ctl + up(NSLOT * sizeof(fx::QueueCtl));
   const size_t off_ring = off_bstate + up((size_t)n * sizeof(int2));
   const size_t off_perm = off_ring + up(ring_words * sizeof(unsigned long long));
   const size_t off_spec = off_perm + up((size_t)n * sizeof(int));
@@ -699,6 +707,23 @@ int solve_impl(int64_t n, const int32_t* model_id, const double* params, const d
       fk->timed[m] = timing;
       FX_CUDA(cudaEventRecord(fk->done[m], fk->streams[m]));
       FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
+    }
+#ifndef FX_NO_RESERVE
+#define FX_NO_RESERVE 0
+#endif
+    if (n_regions > 1 && !FX_NO_RESERVE) {
+      // mixed batch: the reserve launches (fx_solve.cuh), after every first launch so that those get the SMs first
+      for (int m = 0; m < FX_NUM_MODELS; m++) {
+        if (!((mask >> m) & 1u)) continue;
+        FX_CUDA(cudaStreamWaitEvent(fk->reserve[m], fk->begin, 0));
+        a.slot = m;
+        a.ring_region = region_of[m];
+        a.reserve = 1;
+        if ((rc = launch_by_id(m, a, geom, n, di.sms, fk->reserve[m]))) return rc;
+        FX_CUDA(cudaEventRecord(fk->rdone[m], fk->reserve[m]));
+        FX_CUDA(cudaStreamWaitEvent(s, fk->rdone[m], 0));
+      }
+      a.reserve = 0;
     }
     if (timing) {
       std::lock_guard<std::mutex> lk2(g_fork_mu);

@@ -76,6 +76,9 @@ FX_HD void derive_params(const double* p, double (&d)[NDERIVED], const MathTab& 
     d[5] = dT;
     d[6] = 1.0 / dT;
     d[7] = 1.0 / p[3];
+  } else if constexpr (MODEL == FX_TABULATED) {
+    d[0] = p[0];  // the table's address, bit-cast
+    d[1] = p[1];  // number of knots
   } else if constexpr (MODEL == FX_LETXS) {
     double Ks = p[6], alpha = p[7], tr = p[8], ts = p[9];
     double dT = ts - tr;
@@ -190,6 +193,39 @@ FX_HD void eval_D(const double (&d)[NDERIVED], double theta, bool want2, double&
       double rho1 = fma(-Tx * ioms, ioms, Lx * iSe * iSe);
       double R2 = R * fma(rho, rho, rho1);
       D2 = -Dwt * fma(-2.0 * R1 * R1, qq, R2) * qq * qq * idT * idT;
+    }
+  } else if constexpr (MODEL == FX_TABULATED) {
+    // D = -(o_1 (I - c))/2 with o(theta) the PCHIP of the profile's inverse, o_k its k-th derivative and I its
+    // antiderivative (interpolated.py:59-67): the local cubic of scipy/interpax's PPoly and what jax.grad makes of
+    // it.  Knots: theta ascending | o | do/dtheta | I - c, n doubles each.
+    const double* tab = reinterpret_cast<const double*>((uintptr_t)f64_bits(d[0]));
+    const long long n = (long long)d[1];
+    D = D1 = iD = fx_nan();
+    D2 = want2 ? fx_nan() : 0.0;
+    if (tab != nullptr && n >= 2) {  // (a lane that never held a problem evaluates with an all-zero block)
+      const double *x = tab, *y = tab + n, *s = tab + 2 * n, *A = tab + 3 * n;
+      if (theta >= x[0] && theta <= x[n - 1]) {  // extrapolate=False; a NaN theta fails both
+        long long lo = 0, hi = n;  // searchsorted(x, theta, side="right") - 1, clipped to [0, n-2]
+        while (lo < hi) {
+          const long long mid = (lo + hi) >> 1;
+          if (x[mid] <= theta) lo = mid + 1; else hi = mid;
+        }
+        long long k = lo - 1;
+        k = k < 0 ? 0 : (k > n - 2 ? n - 2 : k);
+        const double x0 = x[k], y0 = y[k], d0 = s[k];
+        const double h = x[k + 1] - x0, m = (y[k + 1] - y0) / h;
+        const double t = (d0 + s[k + 1] - 2.0 * m) / h;
+        const double c0 = t / h, c1 = (m - d0) / h - t;
+        const double u = theta - x0;
+        const double o = ((c0 * u + c1) * u + d0) * u + y0;
+        const double o1 = (3.0 * c0 * u + 2.0 * c1) * u + d0;
+        const double o2 = 6.0 * c0 * u + 2.0 * c1;
+        const double I = A[k] + (((c0 * 0.25 * u + c1 * (1.0 / 3.0)) * u + d0 * 0.5) * u + y0) * u;
+        D = -(o1 * I) * 0.5;
+        D1 = -(o2 * I + o1 * o) * 0.5;
+        if (want2) D2 = -((6.0 * c0) * I + 2.0 * (o2 * o) + o1 * o1) * 0.5;
+        iD = fx_rcp(D);
+      }
     }
   } else if constexpr (MODEL == FX_LETXS) {
     double Lw = d[0], lnEw = d[1], Tw = d[2], Ls = d[3], lnEs = d[4], Ts = d[5], Cc = d[6];

@@ -107,6 +107,7 @@ struct SolveArgs {
   const unsigned long long* counts;  // per-model bucket sizes (device)
   int slot;                  // this launch's bucket
   int ring_region;           // which of the ring's per-bucket regions it owns (buckets absent from the batch have none)
+  int reserve;               // 1: the bucket's RESERVE launch -- the CTAs its first launch gave up to the other buckets
   const int* perm;           // bucket-major list of problem indices
   const double* params;      // [N][12]
   const double* b;           // [N]  boundary value; with a flow-rate boundary: lower end of the bracket on b
@@ -117,7 +118,7 @@ struct SolveArgs {
   int* counters;             // [N][8]; likewise
   double* knots;             // [N][k_max][4] or nullptr
   int k_max;
-  QueueCtl* ctl;             // [8]
+  QueueCtl* ctl;             // [FX_NUM_MODELS + 1]
   unsigned long long* ring;  // task ring shared by the buckets (each owns a region)
   long long ring_pad;        // spare entries per bucket beyond its problem count
   int2* bstate;              // [N]: .x = phase | lo_neg << 2 | n_bis << 3, .y = speculation slot + 1
@@ -177,6 +178,7 @@ __device__ __forceinline__ double node_midpoint(double lower, double upper, int 
 template <int MODEL>
 struct DerivedCount {
   static constexpr int value = MODEL == FX_CONSTANT ? 2 : MODEL == FX_POWER_LAW ? 4 : MODEL == FX_LOG ? 2 :
+                               MODEL == FX_TABULATED ? 2 :
                                MODEL == FX_BROOKS_COREY ? 6 : MODEL == FX_VAN_GENUCHTEN ? 9 :
                                MODEL == FX_LETD ? 8 : 11;
 };
@@ -216,6 +218,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     dst = reinterpret_cast<double*>(&mt);
     for (int k = tid; k < (int)(sizeof(MathTab) / sizeof(double)); k += SOLVE_BLOCK) dst[k] = src[k];
   }
+#pragma unroll
+  for (int k = 0; k < NDP; k++) s_dpar[k][tid] = 0.0;  // every lane evaluates the model on every trip, work or not
   __syncthreads();
 
   const unsigned lane = tid & 31;
@@ -230,10 +234,15 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
   if (tid == 0) {
     long long off = 0, total = 0;
     for (int k = 0; k < A.slot; k++) off += (long long)A.counts[k];
-    for (int k = 0; k < 8; k++) total += (long long)A.counts[k];
+    for (int k = 0; k <= FX_NUM_MODELS; k++) total += (long long)A.counts[k];
     ctx.n_work = (long long)A.counts[A.slot];
     long long share = total > 0 ? (ctx.n_work * (long long)gridDim.x + total - 1) / total : 0;
     if (ctx.n_work > 0 && share < 1) share = 1;
+    // The shares follow the buckets' problem COUNTS; their work per problem differs (Brooks-Corey takes 1.6x the
+    // right-hand sides of LETd in config C3), so one bucket finishes first and its SMs would idle.  Every bucket
+    // of a mixed batch therefore has a second, reserve launch holding the CTAs it did not get: they are
+    // dispatched as the CTAs of finished buckets leave, and join the same queue.
+    if (A.reserve) share = (long long)gridDim.x - share;
     if ((long long)blockIdx.x >= share) ctx.n_work = 0;  // this CTA is not needed
     ctx.perm = A.perm + off;
     ctx.ctl = A.ctl + A.slot;
@@ -542,14 +551,22 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       // A FROZEN integrator: if this attempt leaves (t0, y0, f(t0, y0), h) bit for bit as it found them, the next
       // attempt -- a pure function of that state -- repeats it exactly, and so does every one after it, until
       // max_ode_steps ends the shot without an event.  That is how a too-steep shot dies against a sharp front:
-      // the step size underflows (t0 + dt == t0, h = 0) within a few hundred attempts and the remaining
-      // ~3700 of diffrax's 4096 are copies, each "accepted".  They are counted, not integrated: same
-      // residual, same counters, same knots (the CPU twin runs them all; the tests demand bit equality).
-      bool frozen;
-      {
+      // within a few hundred attempts either the step underflows (t0 + dt == t0, h = 0: every further attempt is
+      // "accepted" and moves nothing) or it settles at one ulp of t0 with the error test rejecting it and the
+      // controller proposing 0.85 ulp, which rounds back to one ulp -- and the remaining ~3700 of diffrax's 4096
+      // attempts are copies.  They are counted, not integrated: same residual, same counters, same knots (the CPU
+      // twin runs them all; the tests demand bit equality).
+      bool frozen = false;
+#ifndef FX_FROZEN_FF
+#define FX_FROZEN_FF 1
+#endif
+      if (FX_FROZEN_FF) {
+        // necessary, cheap and almost never true: the next step equals this one (h = 0, or stuck at one ulp of t0)
         const double nt0 = s.keep ? t1 : t0;
-        const bool same_f = !s.keep || (f0 == fsm[0][tid][0] && f1 == fsm[0][tid][1]);
-        frozen = (nt0 == t0) && (s.y10 == y00) && (s.y11 == y01) && same_f && (((nt0 + s.dt_next) - nt0) == h);
+        if (((nt0 + s.dt_next) - nt0) == h) {
+          // a rejected attempt changes nothing but the step; an accepted one must reproduce t0, y0 and f(t0, y0)
+          frozen = !s.keep || (t1 == t0 && s.y10 == y00 && s.y11 == y01 && f0 == fsm[0][tid][0] && f1 == fsm[0][tid][1]);
+        }
       }
       const int rhs_att = rhs_shot - rhs_mark;  // right-hand sides of this attempt
       rhs_mark = rhs_shot;
@@ -719,7 +736,10 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
             // Ring entries pushed and not yet popped must never exceed its capacity (the bucket's problems
             // + one spare entry per resident lane).  Batches sized to fill the lanes stay far below it; as
             // insurance no batch is pushed into a ring that is already half full.
-            if (d > 1) {
+#ifndef FX_RING_GUARD
+#define FX_RING_GUARD 1
+#endif
+            if (FX_RING_GUARD && d > 1) {
               const unsigned long long tl = *(volatile unsigned long long*)&ctx.ctl->tail;
               unsigned long long hd = *(volatile unsigned long long*)&ctx.ctl->head;
               if (hd < (unsigned long long)ctx.n_work) hd = (unsigned long long)ctx.n_work;
@@ -757,7 +777,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
 // sets each bucket's queue control block from the bucket sizes (one thread per bucket)
 __global__ void init_queues_kernel(const unsigned long long* counts, QueueCtl* ctl) {
   int m = threadIdx.x;
-  if (m < 8) {
+  if (m <= FX_NUM_MODELS) {
     long long n = (long long)counts[m];
     ctl[m].head = 0;
     ctl[m].tail = (unsigned long long)n;

@@ -239,13 +239,36 @@ class LETxs(_TaggedModel):
                 self.theta_range[0], self.theta_range[1]]
 
 
+class Tabulated(_TaggedModel):
+    """The diffusivity a measured profile implies, ``InterpolatedSolution.D``
+    (src/frontx/_inverse/interpolated.py:59-67), as a model the kernels know -- so that it can be fed back into
+    ``solve`` like the reference's ``solve(D=sol.D, ...)`` (tests/test_inverse.py:42-48).
+
+    ``table`` is a contiguous CUDA float64 tensor ``[4, n]``: theta ascending, o, do/dtheta at the knots and
+    ``Iodtheta - c`` at the knots.  The parameter block carries its device address; this object (and any
+    ``ModelBatch`` made from it) keeps the tensor alive.  ``InterpolatedSolution.tabulated_model()`` builds one.
+    """
+
+    model_id = _lib.TABULATED
+
+    def __init__(self, table: Any) -> None:
+        if table.dim() != 2 or table.shape[0] != 4 or table.shape[1] < 2 or not table.is_cuda or not table.is_contiguous():
+            raise ValueError("table must be a contiguous CUDA float64 tensor of shape [4, n], n >= 2")
+        self.table = table
+
+    def _pack(self):
+        address = np.array([self.table.data_ptr()], dtype=np.uint64).view(np.float64)[0]
+        return [address, float(self.table.shape[1])]
+
+
 class ModelBatch:
     """n tagged models as two arrays: ``model_id[n]`` (int32) and ``params[n, 12]`` (float64)."""
 
-    def __init__(self, model_id: Any, params: Any) -> None:
+    def __init__(self, model_id: Any, params: Any, keepalive: Any = None) -> None:
         self.model_id = np.ascontiguousarray(model_id, dtype=np.int32)
         self.params = np.ascontiguousarray(params, dtype=np.float64).reshape(self.model_id.size, _lib.NPARAM)
         self._dev = None
+        self._keepalive = keepalive  # device tables the parameter blocks point into (Tabulated)
 
     def __len__(self) -> int:
         return int(self.model_id.size)
@@ -260,16 +283,17 @@ class ModelBatch:
                 )
         ids = np.array([m.model_id for m in models], dtype=np.int32)
         par = np.stack([m.params() for m in models]) if models else np.zeros((0, _lib.NPARAM))
-        return ModelBatch(ids, par)
+        return ModelBatch(ids, par, [m.table for m in models if isinstance(m, Tabulated)] or None)
 
     @staticmethod
     def concat(batches: Sequence["ModelBatch"]) -> "ModelBatch":
         return ModelBatch(np.concatenate([b.model_id for b in batches]),
-                          np.concatenate([b.params for b in batches]))
+                          np.concatenate([b.params for b in batches]),
+                          [k for b in batches for k in (b._keepalive or [])] or None)
 
     def __getitem__(self, idx) -> "ModelBatch":
         ids = np.atleast_1d(self.model_id[idx])
-        return ModelBatch(ids, self.params[idx].reshape(ids.size, _lib.NPARAM))
+        return ModelBatch(ids, self.params[idx].reshape(ids.size, _lib.NPARAM), self._keepalive)
 
     def mask(self) -> int:
         """Bit m set = model id m occurs in the batch (``fx_solve_options.model_mask``: only those models are

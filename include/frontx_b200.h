@@ -53,6 +53,13 @@ extern "C" {
  *   FX_LETXS          {Lw, Ew, Tw, Ls, Es, Ts, Ks, alpha, theta_r, theta_s}  models.py:256-315
  *   FX_LETD           {L, E, T, Dwt, theta_r, theta_s}       src/frontx/models.py:35-66
  *   FX_LOG            {c0, c1}      D = c0 + c1*ln(theta)    tests/test_solve.py:40 (Philip 1960)
+ *   FX_TABULATED      {table, n}    D = -(do/dtheta (Iodtheta - c))/2 of a measured profile: what
+ *                                   InterpolatedSolution.D is (src/frontx/_inverse/interpolated.py:59-67), so that it
+ *                                   can be fed back into solve (tests/test_inverse.py:42-48).  `table` is a DEVICE
+ *                                   pointer, bit-cast into the double, to 4 rows of n doubles: theta ascending, o,
+ *                                   do/dtheta at the knots, Iodtheta - c at the knots (fx_unique_batch +
+ *                                   fx_inverse_batch produce them); it must outlive the call.  NaN outside
+ *                                   [theta_0, theta_n-1] (extrapolate=False).
  */
 enum fx_model {
   FX_CONSTANT = 0,
@@ -62,7 +69,8 @@ enum fx_model {
   FX_LETXS = 4,
   FX_LETD = 5,
   FX_LOG = 6,
-  FX_NUM_MODELS = 7
+  FX_TABULATED = 7,
+  FX_NUM_MODELS = 8
 };
 
 /* per-problem status in counters[.][0]; mirrors src/frontx/_forward.py:114-122:

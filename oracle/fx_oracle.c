@@ -143,6 +143,26 @@ static jet D_jet(int model, const double *p, double theta) {
       jet C = j_recip(j_deriv(h));
       return j_div(j_scale(Ks, kr), C);
     }
+    case FXO_TABULATED: { /* interpolated.py:59-67: D = -(do/dtheta (Iodtheta - c))/2, PPoly pieces of scipy/interpax */
+      double bits = p[0];
+      const double *tab;
+      memcpy(&tab, &bits, sizeof tab);
+      int64_t n = (int64_t)p[1];
+      const double *x = tab, *y = tab + n, *s = tab + 2 * n, *A = tab + 3 * n;
+      if (!(theta >= x[0] && theta <= x[n - 1])) { jet nn = {NAN, NAN, NAN, NAN}; return nn; } /* extrapolate=False */
+      int64_t lo = 0, hi = n;
+      while (lo < hi) { int64_t mid = (lo + hi) / 2; if (x[mid] <= theta) lo = mid + 1; else hi = mid; }
+      int64_t k = lo - 1;
+      if (k < 0) k = 0;
+      if (k > n - 2) k = n - 2;
+      double h = x[k + 1] - x[k], m = (y[k + 1] - y[k]) / h, t = (s[k] + s[k + 1] - 2.0 * m) / h;
+      double c0 = t / h, c1 = (m - s[k]) / h - t, c2 = s[k], c3 = y[k], u = theta - x[k];
+      /* jets in theta of the derivative PPoly and of the antiderivative PPoly (power basis, as scipy evaluates them) */
+      jet o1 = {(3.0 * c0 * u + 2.0 * c1) * u + c2, 6.0 * c0 * u + 2.0 * c1, 6.0 * c0, 0.0};
+      jet I = {A[k] + (((c0 / 4.0 * u + c1 / 3.0) * u + c2 / 2.0) * u + c3) * u, ((c0 * u + c1) * u + c2) * u + c3,
+               o1.v, o1.d1};
+      return j_scale(-0.5, j_mul(o1, I));
+    }
     default:
       return j_const(NAN);
   }

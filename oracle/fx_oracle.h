@@ -43,7 +43,9 @@ enum {
   FXO_VAN_GENUCHTEN = 3,  /* p = {n, m, l, Ks, alpha, theta_r, theta_s, form}         */
   FXO_LETXS = 4,          /* p = {Lw, Ew, Tw, Ls, Es, Ts, Ks, alpha, theta_r, theta_s} */
   FXO_LETD = 5,           /* p = {L, E, T, Dwt, theta_r, theta_s}                     */
-  FXO_LOG = 6             /* D = c0 + c1*ln(theta); p = {c0, c1}  (Philip 1960 test)  */
+  FXO_LOG = 6,            /* D = c0 + c1*ln(theta); p = {c0, c1}  (Philip 1960 test)  */
+  FXO_TABULATED = 7       /* InterpolatedSolution.D: p = {HOST pointer (bit-cast) to 4 rows of n doubles --
+                             theta ascending, o, do/dtheta, Iodtheta - c --, n}               */
 };
 
 /* summary[8]  : d_dob, oi, theta(oi), S0=-2 D(b) d_dob, D(b), residual, lower, upper

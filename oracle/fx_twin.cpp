@@ -241,6 +241,7 @@ int flow_dispatch(int model, const double* p, double q, double i, double b_lo, d
     case FX_LETXS: return solve_one_flow<FX_LETXS>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
     case FX_LETD: return solve_one_flow<FX_LETD>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
     case FX_LOG: return solve_one_flow<FX_LOG>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
+    case FX_TABULATED: return solve_one_flow<FX_TABULATED>(p, q, i, b_lo, b_hi, o, summary, counters, k_max, knots);
     default: counters[0] = -1; return -1;
   }
 }
@@ -255,6 +256,7 @@ int solve_dispatch(int model, const double* p, double b, double i, const Options
     case FX_LETXS: return solve_one<FX_LETXS>(p, b, i, o, summary, counters, k_max, knots);
     case FX_LETD: return solve_one<FX_LETD>(p, b, i, o, summary, counters, k_max, knots);
     case FX_LOG: return solve_one<FX_LOG>(p, b, i, o, summary, counters, k_max, knots);
+    case FX_TABULATED: return solve_one<FX_TABULATED>(p, b, i, o, summary, counters, k_max, knots);
     default: counters[0] = -1; return -1;
   }
 }
@@ -312,6 +314,7 @@ void fxt_D(int model, const double* p, double theta, double* out) {
     case FX_LETXS: D_one<FX_LETXS>(p, theta, out); break;
     case FX_LETD: D_one<FX_LETD>(p, theta, out); break;
     case FX_LOG: D_one<FX_LOG>(p, theta, out); break;
+    case FX_TABULATED: D_one<FX_TABULATED>(p, theta, out); break;
     default: out[0] = out[1] = out[2] = fx::fx_nan();
   }
 }

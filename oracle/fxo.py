@@ -20,7 +20,7 @@ LIB = HERE / "libfx_oracle.so"
 
 NPARAM, NSUM, NCNT, KNOT = 12, 8, 8, 5
 
-CONSTANT, POWER_LAW, BROOKS_COREY, VAN_GENUCHTEN, LETXS, LETD, LOG = range(7)
+CONSTANT, POWER_LAW, BROOKS_COREY, VAN_GENUCHTEN, LETXS, LETD, LOG, TABULATED = range(8)
 
 
 class Options(C.Structure):
@@ -273,6 +273,30 @@ def inverse(o, theta):
     s2 = C.c_double()
     rc = lib().fxo_inverse(oo.size, _dp(oo), _dp(th), _dp(Dk), C.byref(s1), C.byref(s2))
     return rc, Dk, s1.value, s2.value
+
+
+def tabulated(o, theta, b=None, i=None):
+    """The table of a FXO_TABULATED model from scipy's own PchipInterpolator / PPoly (what interpax ports), following
+    interpolated.py:30-50 line for line: returns (params[12], table) -- keep `table` alive while the model is in use."""
+    from scipy.interpolate import PchipInterpolator
+
+    o = np.asarray(o, dtype=np.float64)
+    theta = np.asarray(theta, dtype=np.float64)
+    if b is not None:
+        o, theta = np.insert(o, 0, 0), np.insert(theta, 0, b)
+    if i is not None:
+        o, theta = np.append(o, o[-1] + 1), np.append(theta, i)
+    else:
+        i = theta[-1]
+    theta, idx = np.unique(theta, return_index=True)
+    o = o[idx]
+    inv = PchipInterpolator(theta, o, extrapolate=False)
+    anti = inv.antiderivative()
+    table = np.ascontiguousarray(np.stack([theta, o, inv.derivative()(theta), anti(theta) - anti(i)]))
+    p = np.zeros(NPARAM)
+    p[0] = np.array([table.ctypes.data], dtype=np.uint64).view(np.float64)[0]
+    p[1] = theta.size
+    return p, table
 
 
 def vg_form(params, form: str) -> np.ndarray:
