@@ -18,6 +18,12 @@
 #include "fx_inverse.cuh"
 #include "fx_solve.cuh"
 
+// A mixed batch of at least this many problems per resident lane runs its model buckets one after another
+// (see solve_impl); below it they run side by side.  Scheduling only: results do not depend on it.
+#ifndef FX_SEQUENTIAL_FACTOR
+#define FX_SEQUENTIAL_FACTOR 3
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -180,8 +186,8 @@ int launch_by_id(int model, const fx::SolveArgs& a, int geom, long long n_upper,
 struct Fork {
   int dev = -1;
   cudaStream_t owner = nullptr;
-  cudaStream_t streams[FX_NUM_MODELS] = {}, reserve[FX_NUM_MODELS] = {};
-  cudaEvent_t begin = nullptr, done[FX_NUM_MODELS] = {}, rdone[FX_NUM_MODELS] = {};
+  cudaStream_t streams[FX_NUM_MODELS] = {};
+  cudaEvent_t begin = nullptr, done[FX_NUM_MODELS] = {};
   cudaEvent_t k0[FX_NUM_MODELS] = {}, k1[FX_NUM_MODELS] = {};  // kernel timing (fx_set_kernel_timing)
   bool timed[FX_NUM_MODELS] = {};
   std::mutex mu;
@@ -209,9 +215,7 @@ int get_fork(cudaStream_t owner, Fork** out) {
   f->owner = owner;
   for (int m = 0; m < FX_NUM_MODELS; m++) {
     FX_CUDA(cudaStreamCreateWithFlags(&f->streams[m], cudaStreamNonBlocking));
-    FX_CUDA(cudaStreamCreateWithFlags(&f->reserve[m], cudaStreamNonBlocking));
     FX_CUDA(cudaEventCreateWithFlags(&f->done[m], cudaEventDisableTiming));
-    FX_CUDA(cudaEventCreateWithFlags(&f->rdone[m], cudaEventDisableTiming));
     FX_CUDA(cudaEventCreate(&f->k0[m]));
     FX_CUDA(cudaEventCreate(&f->k1[m]));
   }
@@ -691,39 +695,30 @@ int solve_impl(int64_t n, const int32_t* model_id, const double* params, const d
   a.sms = di.sms;
 
   {
-    // fork: one persistent launch per model present, side by side; the set is this call's until the join
+    // One persistent launch per model present.  A batch of a few problems per lane is a latency chain per
+    // problem (~18 sequential shots): its buckets run SIDE BY SIDE on forked streams, each on a share of the
+    // CTAs.  A large mixed batch is throughput: its buckets run ONE AFTER ANOTHER on the caller's stream, each on
+    // the whole grid, so that no SM idles because one model's problems are cheaper than another's.
     std::lock_guard<std::mutex> lk(fk->mu);
     const bool timing = g_kernel_timing.load() != 0;
     const int geom = q ? 2 : (o.radial_k > 0 ? 1 : 0);
-    FX_CUDA(cudaEventRecord(fk->begin, s));
+    const bool sequential = n_regions > 1 && n >= (long long)FX_SEQUENTIAL_FACTOR * di.sms * fx::SOLVE_CTAS_PER_SM * fx::SOLVE_BLOCK;
+    a.full_grid = sequential ? 1 : 0;
+    if (!sequential) FX_CUDA(cudaEventRecord(fk->begin, s));
     for (int m = 0; m < FX_NUM_MODELS; m++) {
       if (!((mask >> m) & 1u)) continue;
-      FX_CUDA(cudaStreamWaitEvent(fk->streams[m], fk->begin, 0));
+      cudaStream_t ks = sequential ? s : fk->streams[m];
+      if (!sequential) FX_CUDA(cudaStreamWaitEvent(ks, fk->begin, 0));
       a.slot = m;
       a.ring_region = region_of[m];
-      if (timing) FX_CUDA(cudaEventRecord(fk->k0[m], fk->streams[m]));
-      if ((rc = launch_by_id(m, a, geom, n, di.sms, fk->streams[m]))) return rc;
-      if (timing) FX_CUDA(cudaEventRecord(fk->k1[m], fk->streams[m]));
+      if (timing) FX_CUDA(cudaEventRecord(fk->k0[m], ks));
+      if ((rc = launch_by_id(m, a, geom, n, di.sms, ks))) return rc;
+      if (timing) FX_CUDA(cudaEventRecord(fk->k1[m], ks));
       fk->timed[m] = timing;
-      FX_CUDA(cudaEventRecord(fk->done[m], fk->streams[m]));
-      FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
-    }
-#ifndef FX_NO_RESERVE
-#define FX_NO_RESERVE 0
-#endif
-    if (n_regions > 1 && !FX_NO_RESERVE) {
-      // mixed batch: the reserve launches (fx_solve.cuh), after every first launch so that those get the SMs first
-      for (int m = 0; m < FX_NUM_MODELS; m++) {
-        if (!((mask >> m) & 1u)) continue;
-        FX_CUDA(cudaStreamWaitEvent(fk->reserve[m], fk->begin, 0));
-        a.slot = m;
-        a.ring_region = region_of[m];
-        a.reserve = 1;
-        if ((rc = launch_by_id(m, a, geom, n, di.sms, fk->reserve[m]))) return rc;
-        FX_CUDA(cudaEventRecord(fk->rdone[m], fk->reserve[m]));
-        FX_CUDA(cudaStreamWaitEvent(s, fk->rdone[m], 0));
+      if (!sequential) {
+        FX_CUDA(cudaEventRecord(fk->done[m], ks));
+        FX_CUDA(cudaStreamWaitEvent(s, fk->done[m], 0));
       }
-      a.reserve = 0;
     }
     if (timing) {
       std::lock_guard<std::mutex> lk2(g_fork_mu);

@@ -107,7 +107,7 @@ struct SolveArgs {
   const unsigned long long* counts;  // per-model bucket sizes (device)
   int slot;                  // this launch's bucket
   int ring_region;           // which of the ring's per-bucket regions it owns (buckets absent from the batch have none)
-  int reserve;               // 1: the bucket's RESERVE launch -- the CTAs its first launch gave up to the other buckets
+  int full_grid;             // 1: the buckets of this batch run one after another, each on every CTA of its grid
   const int* perm;           // bucket-major list of problem indices
   const double* params;      // [N][12]
   const double* b;           // [N]  boundary value; with a flow-rate boundary: lower end of the bracket on b
@@ -238,11 +238,11 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     ctx.n_work = (long long)A.counts[A.slot];
     long long share = total > 0 ? (ctx.n_work * (long long)gridDim.x + total - 1) / total : 0;
     if (ctx.n_work > 0 && share < 1) share = 1;
-    // The shares follow the buckets' problem COUNTS; their work per problem differs (Brooks-Corey takes 1.6x the
-    // right-hand sides of LETd in config C3), so one bucket finishes first and its SMs would idle.  Every bucket
-    // of a mixed batch therefore has a second, reserve launch holding the CTAs it did not get: they are
-    // dispatched as the CTAs of finished buckets leave, and join the same queue.
-    if (A.reserve) share = (long long)gridDim.x - share;
+    // Side by side, the shares follow the buckets' problem COUNTS, not their work (Brooks-Corey takes 1.6x the
+    // right-hand sides of LETd in config C3), so one bucket finishes first and its SMs idle: fine for a batch
+    // that is one latency chain per problem anyway, wasteful for a large one.  Large mixed batches therefore
+    // run their buckets one after another (fx_api.cu), each on the whole grid.
+    if (A.full_grid) share = gridDim.x;
     if ((long long)blockIdx.x >= share) ctx.n_work = 0;  // this CTA is not needed
     ctx.perm = A.perm + off;
     ctx.ctl = A.ctl + A.slot;

@@ -17,7 +17,8 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-gencode", "arch=comp
 VARIANTS = {
     "cur": [],
     "nofrozen": ["-DFX_FROZEN_FF=0"],
-    "noreserve": ["-DFX_NO_RESERVE=1"],
+    "sidebyside": ["-DFX_SEQUENTIAL_FACTOR=1000000"],
+    "seq1": ["-DFX_SEQUENTIAL_FACTOR=1"],
 }
 
 
