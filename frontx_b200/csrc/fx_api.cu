@@ -692,7 +692,6 @@ int solve_impl(int64_t n, const int32_t* model_id, const double* params, const d
   a.max_ode_steps = o.max_ode_steps;
   a.max_expansions = o.max_expansions;
   a.radial_k = o.radial_k;
-  a.sms = di.sms;
 
   {
     // One persistent launch per model present.  A batch of a few problems per lane is a latency chain per

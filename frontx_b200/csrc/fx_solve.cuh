@@ -66,9 +66,12 @@ namespace fx {
 #ifndef FX_SPEC_MAX_DEPTH
 #define FX_SPEC_MAX_DEPTH 5  // up to 2^depth - 1 speculative shots per problem and round
 #endif
-#ifndef FX_TAIL_DENSE
-#define FX_TAIL_DENSE 0      // 1: in the end phase only as many CTA layers as the outstanding shots can fill
-#endif                       // take work (full warps, few warps per scheduler), the rest drain and sleep
+#ifndef FX_SPARSE_NAP
+#define FX_SPARSE_NAP 2000   // ns between the polls of an idle warp in the end phase
+#endif
+#ifndef FX_SPARSE_POLL_MASK
+#define FX_SPARSE_POLL_MASK 63u // a busy warp with free lanes polls every (mask + 1)-th trip in the end phase
+#endif
 constexpr int SOLVE_BLOCK = FX_SOLVE_BLOCK;
 constexpr int SOLVE_CTAS_PER_SM = FX_SOLVE_CTAS;
 constexpr int SPEC_MAX_DEPTH = FX_SPEC_MAX_DEPTH;
@@ -127,7 +130,6 @@ struct SolveArgs {
   unsigned int spec_slots;
   double itol, rtol, atol, ob;
   int max_bisect, max_ode_steps, max_expansions, radial_k;
-  int sms;                   // SMs of the device: CTA b is taken to be the (b / sms)-th resident CTA of its SM
 };
 
 enum Mode : int { M_FETCH = 0, M_DB = 1, M_INIT0 = 2, M_INIT1 = 3, M_CHORD = 4, M_DONE = 5, M_WAIT = 6 };
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
   // registers, not arithmetic, bound the resident warps of this kernel.
   __shared__ double s_dpar[NDP][SOLVE_BLOCK];  // the model's derived constants
   __shared__ double s_cold[FLOW ? 6 : 5][SOLVE_BLOCK];  // b, i, direction, bisection value of the shot, t1, (q)
-  __shared__ int s_cnt[4][SOLVE_BLOCK];        // attempts, rejections, knots of the shot; RHS count at the last attempt's end
+  __shared__ int s_cnt[4][SOLVE_BLOCK];        // attempts, rejections, knots of the shot; RHS count where a frozen attempt ended (-1: none)
   __shared__ BlockCtx ctx;                     // bucket geometry (same for every thread)
 
   const int tid = threadIdx.x;
@@ -288,44 +290,33 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
     // work settle into few full warps instead of many nearly empty ones.
     // In the last rounds (few problems left, each a critical path) the opposite holds: a shot
     // runs fastest in a warp of its own, so busy warps stop taking work and idle ones poll fast.
-    if (need && (!busy || (poll++ & (sparse ? 15u : 1u)) == 0)) {
-      const int leader = __ffs(need) - 1;
-      const int want = __popc(need);
-      long long got = 0;
+    if (need && (!busy || (poll++ & (sparse ? FX_SPARSE_POLL_MASK : 1u)) == 0)) {
+      // The probe is three loads of warp-uniform addresses (one transaction each) and two votes: an idle warp's
+      // poll must cost next to nothing, because in the end phase the polls of the idle warps share the issue
+      // slots with the few shots that are the launch's critical path.  Only when something is waiting does a
+      // leader claim it.
+      QueueCtl* ctl = ctx.ctl;
+      const long long rem = *(volatile long long*)&ctl->remaining;
+      const unsigned int ab = *(volatile unsigned int*)&ctl->abort;
+      const long long av = *(volatile long long*)&ctl->avail;
+      const bool over = __any_sync(FULL, rem <= 0 || ab != 0u);
+      const bool some = !over && __any_sync(FULL, av > 0);
+      sparse = __any_sync(FULL, rem * 16 < ctx.n_lanes);
+      long long got = over ? -1 : 0;
       unsigned long long h0 = 0;
-      bool sparse_now = false;
-      if ((int)lane == leader) {
-        QueueCtl* ctl = ctx.ctl;
-        const long long rem = *(volatile long long*)&ctl->remaining;
-        const unsigned int ab = *(volatile unsigned int*)&ctl->abort;
-        sparse_now = rem * 16 < ctx.n_lanes;
-        bool allowed = true;
-#if FX_TAIL_DENSE
-        if (sparse_now && A.sms > 0 && gridDim.x >= (unsigned)A.sms) {
-          // End phase: the unfinished problems' batches need rem * (2^depth - 1) lanes.  Only the first
-          // `layers` resident CTAs of every SM take work -- full warps on few warp slots per scheduler,
-          // where a trip costs its latency instead of its share of the issue slots -- the rest drain.
-          const long long per_layer = (long long)A.sms * SOLVE_BLOCK;
-          const long long want = rem * ((1LL << SPEC_MAX_DEPTH) - 1);
-          const long long layers = (want + per_layer - 1) / per_layer;
-          allowed = (long long)(blockIdx.x / (unsigned)A.sms) < (layers < 1 ? 1 : layers);
-          sparse_now = false;  // the working CTAs pack their warps
-          if (!allowed) sparse_now = true;
-        }
-#endif
-        if (rem <= 0 || ab) {
-          got = -1;
-        } else if (allowed && *(volatile long long*)&ctl->avail > 0) {
+      if (some) {
+        const int leader = __ffs(need) - 1;
+        const int want = __popc(need);
+        if ((int)lane == leader) {
           long long old = (long long)atomicAdd((unsigned long long*)&ctl->avail,
                                                (unsigned long long)(-(long long)want));
           got = old >= want ? want : (old > 0 ? old : 0);
           if (got < want) atomicAdd((unsigned long long*)&ctl->avail, (unsigned long long)(want - got));
           if (got > 0) h0 = atomicAdd(&ctl->head, (unsigned long long)got);
         }
+        got = __shfl_sync(FULL, got, leader);
+        h0 = __shfl_sync(FULL, h0, leader);
       }
-      got = __shfl_sync(FULL, got, leader);
-      h0 = __shfl_sync(FULL, h0, leader);
-      sparse = __shfl_sync(FULL, (int)sparse_now, leader) != 0;
       if (mode == M_FETCH) {
         const int rank = __popc(need & ((1u << lane) - 1u));
         if (got < 0) {
@@ -409,7 +400,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
               t0 = A.ob;
               y00 = bnd_b;
               y01 = d_shot;
-              att_shot = rej_shot = rhs_shot = rhs_mark = 0;
+              att_shot = rej_shot = rhs_shot = 0;
+              rhs_mark = -1;
               te = t0;
               ye0 = y00;
               ye1 = y01;
@@ -420,7 +412,7 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       }
       if (!busy) {
         if (got == 0) {
-          __nanosleep(sparse ? (FX_TAIL_DENSE ? 4000u : 500u) : idle_ns);
+          __nanosleep(sparse ? (unsigned)FX_SPARSE_NAP : idle_ns);
           if (idle_ns < 16000u) idle_ns *= 2;
         } else {
           idle_ns = 1000u;
@@ -451,7 +443,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       t0 = A.ob;
       y00 = bnd_b;
       y01 = -s_cold[FLOW ? 5 : 0][tid] * iD;
-      att_shot = rej_shot = rhs_shot = rhs_mark = 0;
+      att_shot = rej_shot = rhs_shot = 0;
+      rhs_mark = -1;
       te = t0;
       ye0 = y00;
       ye1 = y01;
@@ -472,7 +465,8 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       t0 = A.ob;
       y00 = bnd_b;
       y01 = d_shot;
-      att_shot = rej_shot = rhs_shot = rhs_mark = 0;
+      att_shot = rej_shot = rhs_shot = 0;
+      rhs_mark = -1;
       te = t0;
       ye0 = y00;
       ye1 = y01;
@@ -495,7 +489,6 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       mode = M_INIT1;
     } else if (mode == M_INIT1) {
       rhs_shot++;
-      rhs_mark = rhs_shot;  // the attempts' right-hand sides are counted from here
       double dt = init_dt(y00, y01, fs(0, 0), fs(0, 1), R.F0, R.F1, h, dsz, tol, mt);
       t1 = t0 + dt;
       h = t1 - t0;
@@ -556,20 +549,26 @@ __global__ void __launch_bounds__(SOLVE_BLOCK, SOLVE_CTAS_PER_SM) shoot_bisect_k
       // controller proposing 0.85 ulp, which rounds back to one ulp -- and the remaining ~3700 of diffrax's 4096
       // attempts are copies.  They are counted, not integrated: same residual, same counters, same knots (the CPU
       // twin runs them all; the tests demand bit equality).
+      // The test must cost nothing where it is false -- it runs once per attempt, in a block few lanes of a warp
+      // execute together: a frozen step is zero or one ulp of t0, which the exponents of h and t0 tell (two integer
+      // instructions); only then is the state compared.  The copies' right-hand sides are those of one attempt:
+      // the first frozen attempt marks where the next one -- a copy -- starts, the second knows the count.
       bool frozen = false;
+      int rhs_att = 0;
 #ifndef FX_FROZEN_FF
 #define FX_FROZEN_FF 1
 #endif
-      if (FX_FROZEN_FF) {
-        // necessary, cheap and almost never true: the next step equals this one (h = 0, or stuck at one ulp of t0)
+      if (FX_FROZEN_FF && (__double2hiint(t0) - __double2hiint(h)) >= (51 << 20)) {
         const double nt0 = s.keep ? t1 : t0;
-        if (((nt0 + s.dt_next) - nt0) == h) {
-          // a rejected attempt changes nothing but the step; an accepted one must reproduce t0, y0 and f(t0, y0)
-          frozen = !s.keep || (t1 == t0 && s.y10 == y00 && s.y11 == y01 && f0 == fsm[0][tid][0] && f1 == fsm[0][tid][1]);
+        // a rejected attempt changes nothing but the step; an accepted one must reproduce t0, y0 and f(t0, y0)
+        const bool same = (((nt0 + s.dt_next) - nt0) == h) &&
+                          (!s.keep || (t1 == t0 && s.y10 == y00 && s.y11 == y01 && f0 == fsm[0][tid][0] && f1 == fsm[0][tid][1]));
+        if (same && rhs_mark >= 0) {
+          frozen = true;
+          rhs_att = rhs_shot - rhs_mark;
         }
+        rhs_mark = same ? rhs_shot : -1;
       }
-      const int rhs_att = rhs_shot - rhs_mark;  // right-hand sides of this attempt
-      rhs_mark = rhs_shot;
       if (s.keep) {
         t0 = t1;
         y00 = s.y10;

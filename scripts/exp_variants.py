@@ -16,9 +16,12 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-gencode", "arch=comp
          "-Xcompiler", "-fPIC", "-shared"]
 VARIANTS = {
     "cur": [],
+    "nap1000": ["-DFX_SPARSE_NAP=1000"],
+    "nap2000": ["-DFX_SPARSE_NAP=2000"],
+    "nap4000": ["-DFX_SPARSE_NAP=4000"],
+    "nap250": ["-DFX_SPARSE_NAP=250"],
+    "nap2000m63": ["-DFX_SPARSE_NAP=2000", "-DFX_SPARSE_POLL_MASK=63u"],
     "nofrozen": ["-DFX_FROZEN_FF=0"],
-    "sidebyside": ["-DFX_SEQUENTIAL_FACTOR=1000000"],
-    "seq1": ["-DFX_SEQUENTIAL_FACTOR=1"],
 }
 
 
