@@ -10,6 +10,7 @@ implementations of the reference, the reference on two backends included).
 
 from __future__ import annotations
 
+import ctypes as C
 import json
 from pathlib import Path
 
@@ -160,3 +161,39 @@ def test_uncertain_dependency_semantics_are_pinned_or_unreached(fxo):
     # the paper sets and the C1 power law never expand
     r = fxo.solve(fxo.POWER_LAW, [1.0, 4.0, 0.0], b=1.0, i=0.1)
     assert r["counters"][2] == 0
+
+
+def test_benchmark_failures_are_jumps_of_the_residual(fxo):
+    """0.46 % of config C2's problems end RESULTS.max_steps_reached (`success_fraction` of the bench line).  They
+    are not short of iterations: the bisection has collapsed the bracket to two ADJACENT doubles, and the residual
+    (_forward.py:97-101) still jumps across them -- on the steep side the front undershoots and the event's
+    second clause (theta < i - itol, _forward.py:76-78) ends the shot with theta - i < -itol by construction, on
+    the shallow side the profile turns (dtheta/do >= 0) well above i.  No d_dob representable in fp64 has
+    |residual| < itol, so any faithful implementation of the reference's bisection fails there too; the literal
+    oracle fails on the same problems (up to the handful whose decisions the van Genuchten form flips)."""
+    n = 4000
+    mb = vg_sweep(n)
+    p = mb.params.copy()
+    tw = fxo.twin_solve_batch(mb.model_id, p, B_PAPER, I_PAPER)
+    fail = tw["counters"][:, 0] == 1
+    assert 5 <= fail.sum() <= 40 and (tw["counters"][~fail, 0] == 0).all()
+    S = tw["summary"][fail]
+    lower, upper, res = S[:, 6], S[:, 7], S[:, 5]
+    adjacent = np.nextafter(np.minimum(lower, upper), np.inf) == np.maximum(lower, upper)
+    assert adjacent.all()
+    assert (np.abs(res) >= 1e-3).all() and (tw["counters"][fail, 1] == 102).all()
+    lit = fxo.solve_batch(mb.model_id, p, B_PAPER, I_PAPER)
+    lit_fail = lit["counters"][:, 0] == 1
+    assert (lit_fail ^ fail).sum() <= 3
+    # the literal oracle's own collapsed brackets, both ends shot again by it: one undershoots
+    # (theta_end - i < -itol), the other turns above i
+    Sl = lit["summary"][lit_fail]
+    assert (np.nextafter(np.minimum(Sl[:, 6], Sl[:, 7]), np.inf) == np.maximum(Sl[:, 6], Sl[:, 7])).all()
+    for j in np.flatnonzero(lit_fail)[:6]:
+        ends = []
+        for d in (lit["summary"][j, 6], lit["summary"][j, 7]):
+            cnt = np.zeros(8, dtype=np.int32)
+            nk = C.c_int()
+            ends.append(fxo.lib().fxo_shoot(int(mb.model_id[j]), fxo._dp(fxo.pad_params(p[j])), B_PAPER, I_PAPER, 1e-3,
+                                            float(d), None, 0, None, C.byref(nk), fxo._ip(cnt)))
+        assert min(ends) < -1e-3 and max(ends) > 1e-3, ends
