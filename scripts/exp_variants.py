@@ -16,11 +16,9 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-gencode", "arch=comp
          "-Xcompiler", "-fPIC", "-shared"]
 VARIANTS = {
     "cur": [],
-    "nap1000": ["-DFX_SPARSE_NAP=1000"],
-    "nap2000": ["-DFX_SPARSE_NAP=2000"],
-    "nap4000": ["-DFX_SPARSE_NAP=4000"],
-    "nap250": ["-DFX_SPARSE_NAP=250"],
-    "nap2000m63": ["-DFX_SPARSE_NAP=2000", "-DFX_SPARSE_POLL_MASK=63u"],
+    "ctas6": ["-DFX_SOLVE_CTAS=6"],
+    "ctas4": ["-DFX_SOLVE_CTAS=4"],
+    "nap500": ["-DFX_SPARSE_NAP=500", "-DFX_SPARSE_POLL_MASK=15u"],
     "nofrozen": ["-DFX_FROZEN_FF=0"],
 }
 
