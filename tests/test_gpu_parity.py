@@ -345,6 +345,28 @@ def test_model_mask_hint():
                                   full.summary.cpu().numpy()[mb.model_id == _lib.LETD])
 
 
+def test_large_mixed_batch_buckets_one_after_another():
+    """A mixed batch of more than ~3 problems per resident lane (2.8e5 on a B200) runs its model buckets one after
+    another on the whole grid instead of side by side (fx_api.cu, FX_SEQUENTIAL_FACTOR).  Scheduling only: the
+    records equal, bit for bit, those of the same problems solved in chunks small enough to take the side-by-side
+    path (themselves checked against the twin above), with and without the model-mask hint."""
+    from frontx_b200 import ModelBatch
+
+    n, chunk = 320_000, 40_000
+    mb = mixed_sweep(n, seed=5)
+    whole = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False)
+    nomask = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, k_max=0, throw=False, options={"model_mask": 0})
+    S, Cn = whole.summary.cpu().numpy(), whole.counters.cpu().numpy()
+    np.testing.assert_array_equal(S, nomask.summary.cpu().numpy())
+    np.testing.assert_array_equal(Cn, nomask.counters.cpu().numpy())
+    for a in range(0, n, chunk):
+        part = fx.solve_batch(ModelBatch(mb.model_id[a:a + chunk], mb.params[a:a + chunk]), b=B_PAPER, i=I_PAPER,
+                              k_max=0, throw=False)
+        np.testing.assert_array_equal(part.summary.cpu().numpy(), S[a:a + chunk])
+        np.testing.assert_array_equal(part.counters.cpu().numpy(), Cn[a:a + chunk])
+    assert (Cn[:, 0] == 0).mean() > 0.99 and set(np.unique(Cn[:, 0])) <= {0, 1}
+
+
 def test_two_host_threads_two_streams(fxo):
     """fx_solve_batch is re-entrant: two host threads on two streams of one device get the results each gets
     alone (per-stream fork sets; the round-1 library shared one set of helper events per device)."""
