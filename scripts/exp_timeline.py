@@ -1,4 +1,5 @@
-"""Developer experiment: finish-time distribution of the problems of one C2 launch (debug build)."""
+"""Developer experiment: finish-time distribution of the problems of one launch (debug build, -DFX_DEBUG_TIMES into
+scripts/_dbg/libfrontx_b200_dbg.so): python scripts/exp_timeline.py N [C2|C3]."""
 import sys
 from pathlib import Path
 
@@ -13,8 +14,9 @@ _lib.LIB_PATH = Path(__file__).resolve().parent / "_dbg" / "libfrontx_b200_dbg.s
 L = _lib.lib()
 dev = torch.device("cuda", 0)
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
-models = bench.c2_workload(N, seed=0)
-opt = _lib.default_options(itol=bench.ITOL)
+CFG = sys.argv[2] if len(sys.argv) > 2 else "C2"
+models = bench.c2_workload(N, seed=0) if CFG == "C2" else bench.c3_rows(np.arange(N))
+opt = _lib.default_options(itol=bench.ITOL, model_mask=models.mask())
 stream = torch.cuda.current_stream(dev)
 ids, par = models.to_device(dev)
 b = torch.full((N,), bench.B_BOUNDARY, dtype=torch.float64, device=dev)
@@ -43,3 +45,9 @@ print("last 10: shots", c[last, 1], "rhs", c[last, 5], "status", c[last, 0])
 for lo, hi in ((0, 10), (10, 20), (20, 30), (30, 40), (40, 60), (60, 80), (80, 120)):
     m = (t >= lo) & (t < hi)
     print(f"  finish in [{lo},{hi}) ms: {int(m.sum())} problems, mean shots {c[m, 1].mean() if m.any() else 0:.1f}")
+
+for m in np.unique(models.model_id):
+    sel = models.model_id == m
+    tm = t[sel]
+    print(f"model {m}: {int(sel.sum())} problems, first finish {tm.min():.1f} ms, p50 {np.percentile(tm, 50):.1f}, p99 {np.percentile(tm, 99):.1f}, "
+          f"p99.9 {np.percentile(tm, 99.9):.1f}, last {tm.max():.1f}; failing {int((c[sel, 0] != 0).sum())}")
