@@ -85,3 +85,25 @@ def mixed_sweep(n: int, seed: int = 1):
     ids[0::2], par[0::2] = bc.model_id, bc.params
     ids[1::2], par[1::2] = ld.model_id, ld.params
     return ModelBatch(ids, par)
+
+
+def family_sweep(which: str, n: int, seed: int = 2):
+    """Random sweeps of the model families BASELINE configs C2/C3 do not cover, with the boundary values they are
+    solved for: (ModelBatch, b, i).  LETxs around the paper set (Gerlero et al. 2022, Table 2); the power law and
+    the logarithmic diffusivity are the families of the reference's analytic tests (tests/test_solve.py:40,151)."""
+    from frontx_b200 import models as M
+
+    rng = np.random.default_rng(seed)
+    lu = lambda lo, hi: np.exp(rng.uniform(np.log(lo), np.log(hi), n))  # noqa: E731
+    if which == "letxs":
+        mb = M.LETxs.batch(Lw=rng.uniform(1.0, 2.5, n), Ew=lu(20.0, 2000.0), Tw=rng.uniform(0.6, 1.5, n),
+                           Ls=rng.uniform(0.3, 1.0, n), Es=lu(50.0, 2000.0), Ts=rng.uniform(0.3, 0.8, n),
+                           Ks=lu(1e-3, 3e-2), theta_range=(0.01176, 0.7))
+        return mb, B_PAPER, I_PAPER
+    if which == "power":
+        mb = M.PowerLaw.batch(k=rng.uniform(0.5, 6.0, n), a=lu(0.1, 10.0), epsilon=lu(1e-6, 1e-3))
+        return mb, 1.0, 0.05
+    if which == "log":
+        mb = M.LogDiffusivity.batch(c0=rng.uniform(0.3, 1.0, n), c1=-rng.uniform(0.1, 0.8, n))
+        return mb, 1.0, 0.01
+    raise ValueError(which)

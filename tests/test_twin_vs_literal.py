@@ -17,7 +17,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 import parity_util as pu
-from conftest import B_PAPER, I_PAPER, mixed_sweep, vg_sweep
+from conftest import B_PAPER, I_PAPER, family_sweep, mixed_sweep, vg_sweep
 
 GOLDEN = json.loads((Path(__file__).parent / "golden" / "diffusivity_golden.json").read_text())
 
@@ -128,6 +128,32 @@ def test_sweep_twin_vs_literal_explained(fxo, which, form):
     # sorptivity = -2 D(b) d_dob with d_dob a bisection midpoint: 1e-6 wherever the bisection took the same path
     assert (rel_S[same] < 1e-6).all()
     assert (rel_S < 1e-6).mean() >= 0.99
+
+
+@pytest.mark.parametrize("which", ["letxs", "power", "log"])
+def test_other_families(fxo, which):
+    """The families C2/C3 do not sweep (tests/conftest.py::family_sweep): product arithmetic (twin) vs the
+    literal oracle on theta(o) (128 points) and the sorptivity, per problem.  The power law and the logarithmic
+    diffusivity of the reference's analytic tests are well conditioned at their boundary values: same discrete
+    decisions on every problem and 1e-6 met OUTRIGHT.  LETxs around the paper set at b = theta_s - 1e-7 meets it
+    on all but a few per thousand, each explained the way the C2/C3 sweeps are (a flipped decision, or a problem
+    the oracle itself does not reproduce to 1e-7 when one input moves by one ulp)."""
+    mb, b, i = family_sweep(which, 600)
+    lit = fxo.solve_batch(mb.model_id, mb.params, b, i, k_max=512)
+    tw = fxo.twin_solve_batch(mb.model_id, mb.params, b, i, k_max=512)
+    assert (lit["counters"][:, 0] == tw["counters"][:, 0]).all() and (lit["counters"][:, 0] == 0).mean() > 0.99
+    same = pu.same_decisions(tw, lit)
+    dev = pu.profile_deviation(fxo, tw, lit)
+    rel_S = np.abs(tw["summary"][:, 3] / lit["summary"][:, 3] - 1)
+    print(f"\n{which}: same decisions {same.mean():.4f}, within 1e-6 {(dev < 1e-6).mean():.4f}, "
+          f"max |theta - theta_oracle| {dev.max():.2e}, max rel sorptivity {rel_S.max():.2e}")
+    if which == "letxs":
+        _, self_dev = pu.conditioning(fxo, mb.model_id, mb.params, b, i, lit, 512)
+        unexplained = (dev >= 1e-6) & same & ~(self_dev.max(axis=0) >= 1e-7)
+        assert not unexplained.any(), np.where(unexplained)[0][:10]
+        assert same.mean() >= 0.99 and (dev < 1e-6).mean() >= 0.99 and (rel_S[same] < 1e-6).all()
+    else:
+        assert same.all() and dev.max() < 1e-6 and rel_S.max() < 1e-6
 
 
 def test_uncertain_dependency_semantics_are_pinned_or_unreached(fxo):
