@@ -107,3 +107,12 @@ def family_sweep(which: str, n: int, seed: int = 2):
         mb = M.LogDiffusivity.batch(c0=rng.uniform(0.3, 1.0, n), c1=-rng.uniform(0.1, 0.8, n))
         return mb, 1.0, 0.01
     raise ValueError(which)
+
+
+def interior_boundaries(n: int, seed: int = 11):
+    """Per-problem boundary values away from saturation, 40 % of them reversed (i > b: drainage): (b, i)."""
+    rng = np.random.default_rng(seed)
+    b = rng.uniform(0.3, 0.69, n)
+    i = rng.uniform(0.03, 0.25, n)
+    swap = rng.random(n) < 0.4
+    return np.where(swap, i, b), np.where(swap, b, i)

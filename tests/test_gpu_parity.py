@@ -322,6 +322,53 @@ def test_other_families_sweep(fxo, which):
         assert same.all() and dev.max() < 1e-6 and rel_S.max() < 1e-6
 
 
+@pytest.mark.parametrize("which", ["vg", "mixed"])
+def test_interior_boundary_values(fxo, which):
+    """Per-problem b and i arrays away from saturation, 40 % reversed (tests/conftest.py::interior_boundaries):
+    GPU vs twin bit for bit; against the literal oracle the same decisions on EVERY problem and theta(o) (128
+    points) and sorptivity within 1e-6 on EVERY problem -- the north star met outright where the reference's
+    answer is well conditioned."""
+    from conftest import interior_boundaries
+
+    n = 3000
+    mb = vg_sweep(n, seed=10) if which == "vg" else mixed_sweep(n, seed=9)
+    b, i = interior_boundaries(n)
+    gpu = fx.solve_batch(mb, b=b, i=i, k_max=512, throw=False)
+    rec = pu.as_record(gpu)
+    twin = fxo.twin_solve_batch(mb.model_id, mb.params, b, i, k_max=512)
+    np.testing.assert_array_equal(rec["counters"], twin["counters"])
+    np.testing.assert_array_equal(rec["summary"], twin["summary"])
+    assert_knots_equal(rec["knots"], twin["knots"], twin["counters"][:, 7])
+    ref = fxo.solve_batch(mb.model_id, mb.params, b, i, k_max=512)
+    assert (rec["counters"][:, 0] == 0).all() and (ref["counters"][:, 0] == 0).all()
+    assert pu.same_decisions(rec, ref).all()
+    dev = pu.profile_deviation(fxo, rec, ref)
+    rel_S = np.abs(rec["summary"][:, 3] / ref["summary"][:, 3] - 1)
+    print(f"\n{which}: max |theta - theta_oracle| {dev.max():.2e}, max rel sorptivity {rel_S.max():.2e}")
+    assert dev.max() < 1e-6 and rel_S.max() < 1e-6
+
+
+@pytest.mark.parametrize("itol,max_steps", [(1e-2, 100), (1e-4, 100), (1e-5, 100), (1e-3, 12), (1e-3, 3)])
+def test_itol_and_max_steps_options(fxo, itol, max_steps):
+    """solve(..., itol=, max_steps=) (_forward.py:60-72): the tolerance enters the bisection's stopping rule AND the
+    event; a small max_steps ends most problems as RESULTS.max_steps_reached.  GPU vs twin bit for bit (summaries,
+    counters, knots) on both benchmark distributions; against the literal oracle the same status on (nearly) every
+    problem and the same number of shooting iterations."""
+    for mb in (vg_sweep(600, seed=7), mixed_sweep(600, seed=8)):
+        gpu = fx.solve_batch(mb, b=B_PAPER, i=I_PAPER, itol=itol, max_steps=max_steps, k_max=512, throw=False)
+        rec = pu.as_record(gpu)
+        twin = fxo.twin_solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER, itol=itol, max_steps=max_steps, k_max=512)
+        np.testing.assert_array_equal(rec["counters"], twin["counters"])
+        np.testing.assert_array_equal(rec["summary"], twin["summary"])
+        assert_knots_equal(rec["knots"], twin["knots"], twin["counters"][:, 7])
+        ref = fxo.solve_batch(mb.model_id, mb.params, B_PAPER, I_PAPER, itol=itol, max_steps=max_steps, k_max=512)
+        assert (rec["counters"][:, 0] == ref["counters"][:, 0]).mean() >= 0.99
+        assert (rec["counters"][:, 1] == ref["counters"][:, 1]).mean() >= 0.97
+        assert (rec["counters"][:, 1] <= max_steps + 2).all()
+        ok = (rec["counters"][:, 0] == 0) & (ref["counters"][:, 0] == 0)
+        assert (np.abs(rec["summary"][ok, 5]) < itol).all()  # converged means |theta(oi) - i| < itol
+
+
 @pytest.mark.parametrize("form", ["literal", "expm1"])
 def test_vg_sweep_parity(fxo, form):
     """C2 at N=3000, both forms of 1 - Se^(1/m) (the reference's literal subtraction is the default).  Bitwise
