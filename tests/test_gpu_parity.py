@@ -592,6 +592,24 @@ def test_full_size_bitwise_vs_twin_c2(fxo):
     np.testing.assert_array_equal(sol.summary.cpu().numpy().view(np.int64), tw["summary"].view(np.int64))
 
 
+def test_large_c3_bitwise_vs_twin(fxo):
+    """300 000 problems of BASELINE config C3 (bench.c3_rows: the generator the benchmark uses) -- large enough for
+    the one-after-another bucket path, with the frozen-integrator fast-forward and the replay of repeated shots at
+    scale: summaries and counters equal the twin's bit for bit (the twin needs ~45 s on the box's host cores)."""
+    import bench
+
+    n = 300_000
+    mb = bench.c3_rows(np.arange(n))
+    tw = fxo.twin_solve_batch(mb.model_id, mb.params, bench.B_BOUNDARY, bench.I_INITIAL)
+    sol = fx.solve_batch(mb, b=bench.B_BOUNDARY, i=bench.I_INITIAL, k_max=0, throw=False)
+    np.testing.assert_array_equal(sol.counters.cpu().numpy(), tw["counters"])
+    np.testing.assert_array_equal(sol.summary.cpu().numpy().view(np.int64), tw["summary"].view(np.int64))
+    # successful problems whose few shots nevertheless took >= 3 x 4096 step attempts: shots that ran into diffrax's
+    # attempt limit with a frozen step (the fast-forward's case)
+    long_shots = (tw["counters"][:, 3] >= 3 * 4096) & (tw["counters"][:, 0] == 0)
+    assert long_shots.any()
+
+
 def test_full_size_properties_c2():
     n = 100_000
     models = vg_sweep(n)
