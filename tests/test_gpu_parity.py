@@ -1025,3 +1025,16 @@ def test_reference_test_interpolated_exact_solve(fxo):
     print(f"\nsolve(D=sol.D): {theta.result.name}, d_dob {theta.d_dob:.6f}, max |theta - exp(-o)| = {err:.3e}")
     assert err < (1e-2 if theta.result == fx.RESULTS.successful else 4e-2)
     assert abs(theta.d_dob + 1.0) < 0.07
+
+
+def test_readme_example_runs():
+    """The usage example of README.md, executed as written."""
+    import re
+    from pathlib import Path
+
+    text = (Path(__file__).resolve().parents[1] / "README.md").read_text()
+    block = re.search(r"```python\n(.*?)```", text, re.S).group(1)
+    ns: dict = {}
+    exec(compile(block, "README.md", "exec"), ns)  # noqa: S102
+    assert len(ns["many"]) == 100_000 and float(ns["sol"].d_dob) < 0
+    assert ns["prof"].D(ns["theta_query"]).shape == (50,)
