@@ -116,3 +116,28 @@ def interior_boundaries(n: int, seed: int = 11):
     i = rng.uniform(0.03, 0.25, n)
     swap = rng.random(n) < 0.4
     return np.where(swap, i, b), np.where(swap, b, i)
+
+
+def all_families(n_each: int, seed: int = 21):
+    """Every closed-form family in ONE batch, interleaved, each problem with the boundary values of its family:
+    (ModelBatch, b[n], i[n])."""
+    from frontx_b200 import ModelBatch
+    from frontx_b200 import models as M
+
+    parts = []
+    vg = vg_sweep(n_each, seed=seed)
+    parts.append((vg, np.full(n_each, B_PAPER), np.full(n_each, I_PAPER)))
+    mx = mixed_sweep(2 * n_each, seed=seed + 1)
+    parts.append((mx, np.full(2 * n_each, B_PAPER), np.full(2 * n_each, I_PAPER)))
+    for k, which in enumerate(("letxs", "power", "log")):
+        mb, b, i = family_sweep(which, n_each, seed=seed + 2 + k)
+        parts.append((mb, np.full(n_each, b), np.full(n_each, i)))
+    rng = np.random.default_rng(seed + 9)
+    const = M.Constant.batch(D0=np.exp(rng.uniform(np.log(1e-3), np.log(10.0), n_each)))
+    parts.append((const, np.full(n_each, 1.0), np.full(n_each, 0.0)))
+    ids = np.concatenate([p[0].model_id for p in parts])
+    par = np.concatenate([p[0].params for p in parts])
+    b = np.concatenate([p[1] for p in parts])
+    i = np.concatenate([p[2] for p in parts])
+    order = rng.permutation(ids.size)
+    return ModelBatch(ids[order], par[order]), b[order], i[order]

@@ -445,6 +445,36 @@ def test_large_mixed_batch_buckets_one_after_another():
     assert (Cn[:, 0] == 0).mean() > 0.99 and set(np.unique(Cn[:, 0])) <= {0, 1}
 
 
+def test_all_families_in_one_batch(fxo):
+    """Seven model buckets in one call (constant, power law, Brooks-Corey, van Genuchten, LETxs, LETd, logarithmic),
+    shuffled, each problem with its family's boundary values: bit for bit the twin's records, with dense output;
+    then 7 x 45 000 problems -- the one-after-another path with seven buckets -- equal the same problems solved in
+    chunks that take the side-by-side path."""
+    from conftest import all_families
+    from frontx_b200 import ModelBatch
+
+    mb, b, i = all_families(1500)
+    assert len(set(mb.model_id.tolist())) == 7
+    gpu = fx.solve_batch(mb, b=b, i=i, k_max=512, throw=False)
+    rec = pu.as_record(gpu)
+    twin = fxo.twin_solve_batch(mb.model_id, mb.params, b, i, k_max=512)
+    np.testing.assert_array_equal(rec["counters"], twin["counters"])
+    np.testing.assert_array_equal(rec["summary"], twin["summary"])
+    assert_knots_equal(rec["knots"], twin["knots"], twin["counters"][:, 7])
+    assert (rec["counters"][:, 0] == 0).mean() > 0.99
+
+    big, b2, i2 = all_families(45_000, seed=33)
+    n = len(big)
+    whole = fx.solve_batch(big, b=b2, i=i2, k_max=0, throw=False)
+    S, Cn = whole.summary.cpu().numpy(), whole.counters.cpu().numpy()
+    chunk = 45_000
+    for a in range(0, n, chunk):
+        part = fx.solve_batch(ModelBatch(big.model_id[a:a + chunk], big.params[a:a + chunk]), b=b2[a:a + chunk],
+                              i=i2[a:a + chunk], k_max=0, throw=False)
+        np.testing.assert_array_equal(part.summary.cpu().numpy(), S[a:a + chunk])
+        np.testing.assert_array_equal(part.counters.cpu().numpy(), Cn[a:a + chunk])
+
+
 def test_two_host_threads_two_streams(fxo):
     """fx_solve_batch is re-entrant: two host threads on two streams of one device get the results each gets
     alone (per-stream fork sets; the round-1 library shared one set of helper events per device)."""
