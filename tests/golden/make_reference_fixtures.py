@@ -50,10 +50,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1000, help="problems of each of C2 and C3")
     args = ap.parse_args()
-    import jax
+    try:
+        import jax
 
-    jax.config.update("jax_enable_x64", True)
-    import frontx
+        jax.config.update("jax_enable_x64", True)
+        import frontx
+    except ImportError as e:
+        raise SystemExit(f"this script needs the reference itself (jax, diffrax, optimistix, interpax, frontx): {e}") from None
 
     import bench
     from tests.conftest import B_PAPER, I_PAPER, paper_models
